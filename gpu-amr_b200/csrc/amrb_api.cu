@@ -1,0 +1,941 @@
+// C-ABI of the device side: memory/sync wrappers, the device patch pool and all kernel launches.
+// See include/gpuamr_b200.h for the contract and the reference interfaces each group replaces.
+#include "amrb_kernels.cuh"
+
+#include "../../include/gpuamr_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace amrb
+{
+
+thread_local std::string g_error;
+
+static amrb_status fail(amrb_status code, const std::string& what)
+{
+    g_error = what;
+    return code;
+}
+
+#define AMRB_CUDA(expr)                                                                          \
+    do                                                                                           \
+    {                                                                                            \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(AMRB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+#define AMRB_TRY(expr)                                                                           \
+    do                                                                                           \
+    {                                                                                            \
+        amrb_status s_ = (expr);                                                                 \
+        if (s_ != AMRB_OK) return s_;                                                            \
+    } while (0)
+
+// ---------------------------------------------------------------------------------- kernel dispatch
+struct Ops
+{
+    int    rank, size, halo, eq;
+    int    bands;      // CTAs per patch in the fused step
+    size_t step_smem;  // dynamic shared memory of the fused step
+    cudaError_t (*prepare)();
+    void (*halo_fill)(cudaStream_t, const FieldPtrs&, const int32_t*, const uint8_t*, int);
+    void (*step)(cudaStream_t, const StepArgs&, int n_items);
+    void (*compute_dt)(cudaStream_t, const StepArgs&, unsigned long long*);
+    void (*plan)(cudaStream_t, const FieldPtrs&, const FieldPtrs&, const int8_t*, const int32_t*,
+                 const int8_t*, int);
+    void (*flags)(cudaStream_t, const double*, const int32_t*, int, double, double, int, int,
+                  int8_t*);
+    void (*interior)(cudaStream_t, double*, double*, int, int);
+    void (*faces)(cudaStream_t, const FieldPtrs&, const int32_t*, int, double*, int);
+};
+
+template <int R, int S, int H, int EQ, int BAND>
+struct Inst
+{
+    using G                 = Geo<R, S, H>;
+    static constexpr int NV = EqTraits<EQ, R>::NV;
+    static constexpr int NW = EqTraits<EQ, R>::NW;
+    static constexpr int NT = 256;
+    static constexpr size_t SMEM =
+        (size_t)(NV + NW) * (BAND + 2) * G::pitch(0) * sizeof(double);
+
+    static cudaError_t prepare()
+    {
+        return cudaFuncSetAttribute(step_kernel<R, S, H, EQ, BAND, NT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    }
+    static void halo_fill(cudaStream_t st, const FieldPtrs& cur, const int32_t* nbr,
+                          const uint8_t* meta, int n)
+    {
+        halo_kernel<R, S, H, NV><<<n, 256, 0, st>>>(cur, nbr, meta, n);
+    }
+    static void step(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        step_kernel<R, S, H, EQ, BAND, NT><<<n_items * (S / BAND), NT, SMEM, st>>>(a);
+    }
+    static void compute_dt(cudaStream_t st, const StepArgs& a, unsigned long long* out)
+    {
+        compute_dt_kernel<R, S, H, EQ, NT>
+            <<<a.n_patches, NT, 0, st>>>(a.cur, a.level, a.n_patches, a.gamma, a, out);
+    }
+    static void plan(cudaStream_t st, const FieldPtrs& o, const FieldPtrs& n, const int8_t* kind,
+                     const int32_t* src, const int8_t* child, int count)
+    {
+        plan_kernel<R, S, H, NV><<<count, 256, 0, st>>>(o, n, kind, src, child, count);
+    }
+    static void flags(cudaStream_t st, const double* field, const int32_t* level, int n,
+                      double rt, double ct, int minl, int maxl, int8_t* out)
+    {
+        patch_max_flags_kernel<G::FLAT><<<n, 128, 0, st>>>(field, level, n, rt, ct, minl, maxl, out);
+    }
+    static void interior(cudaStream_t st, double* padded, double* dense, int n, int to_padded)
+    {
+        interior_copy_kernel<R, S, H><<<n, 256, 0, st>>>(padded, dense, n, to_padded);
+    }
+    static void faces(cudaStream_t st, const FieldPtrs& cur, const int32_t* entries, int count,
+                      double* buffer, int unpack)
+    {
+        face_pack_kernel<R, S, H, NV><<<count, 128, 0, st>>>(cur, entries, count, buffer, unpack);
+    }
+    static constexpr Ops ops()
+    {
+        return Ops{ R,    S,         H,          EQ,   S / BAND, SMEM,     &prepare, &halo_fill,
+                    &step, &compute_dt, &plan, &flags, &interior, &faces };
+    }
+};
+
+// (rank, size, halo, band) for both equations.  Patch shapes of the reference's drivers:
+// 10x10/h2 (examples/fvm_solver_advection.e.cpp:24-53), 64x64/h1 (benchmark/
+// bench_fvm_solver_integration.b.cpp:34-63), 8^3/h1 (bench_fvm_solver_integration3D.b.cpp:31-64),
+// 16x16/h1 (KA-2D), plus the small shapes used by the parity fixtures.
+#define AMRB_SHAPES(X)                                                                           \
+    X(2, 8, 1, 8)                                                                                \
+    X(2, 10, 2, 10)                                                                              \
+    X(2, 16, 1, 16)                                                                              \
+    X(2, 32, 1, 16)                                                                              \
+    X(2, 64, 1, 16)                                                                              \
+    X(3, 4, 1, 4)                                                                                \
+    X(3, 4, 2, 4)                                                                                \
+    X(3, 8, 1, 8)                                                                                \
+    X(3, 16, 1, 4)
+
+static const Ops g_ops[] = {
+#define X(R, S, H, B) Inst<R, S, H, kEqAdvection, B>::ops(), Inst<R, S, H, kEqEuler, B>::ops(),
+    AMRB_SHAPES(X)
+#undef X
+};
+
+static const Ops* find_ops(const amrb_layout& l)
+{
+    if (l.rank != 2 && l.rank != 3) return nullptr;
+    for (int k = 1; k < l.rank; ++k)
+        if (l.size[k] != l.size[0]) return nullptr; // cubic patches only
+    const int nv = (l.equation == AMRB_EQ_ADVECTION) ? 1 : l.rank + 2;
+    if (l.nvar != nv) return nullptr;
+    for (const Ops& o : g_ops)
+        if (o.rank == l.rank && o.size == l.size[0] && o.halo == l.halo && o.eq == l.equation)
+            return &o;
+    return nullptr;
+}
+
+} // namespace amrb
+
+using namespace amrb;
+
+// ---------------------------------------------------------------------------------- pool
+struct amrb_pool
+{
+    amrb_layout  lay{};
+    const Ops*   ops      = nullptr;
+    int          device   = 0;
+    cudaStream_t stream   = nullptr;
+    bool         own_stream = false, own_mem = false;
+    size_t       capacity = 0, n_owned = 0, n_total = 0, flat = 0, data = 0;
+    FieldPtrs    cur{}, nxt{};
+    int32_t*     d_nbr   = nullptr;
+    uint8_t*     d_meta  = nullptr;
+    int32_t*     d_level = nullptr;
+    size_t       table_cap = 0;
+    double       lengths[3] = { 1.0, 1.0, 1.0 }, gamma = 1.4, cfl = 0.3;
+    double       dx[kMaxLevel + 1][3]{};
+    // batch scalars
+    unsigned long long* d_dtmin = nullptr;
+    double*      d_remaining = nullptr;
+    double*      d_dts       = nullptr;
+    double*      h_dts       = nullptr; // pinned
+    size_t       scal_cap = 0, batch_steps = 0, batch_k = 0;
+    bool         batch_open = false, batch_pending = false, carry_valid = false;
+    bool         step_touched = false;
+    cudaEvent_t  batch_done = nullptr;
+    // staging
+    double*      d_stage = nullptr;
+    size_t       stage_cap = 0;
+    int8_t*      d_flags = nullptr;
+    size_t       flags_cap = 0;
+    void*        d_plan = nullptr;
+    size_t       plan_cap = 0;
+    uint64_t     launches = 0;
+    int          mode     = 0;
+};
+
+namespace
+{
+
+amrb_status set_device(const amrb_pool* p)
+{
+    AMRB_CUDA(cudaSetDevice(p->device));
+    return AMRB_OK;
+}
+
+void compute_dx(amrb_pool* p)
+{
+    // solver/physics_system.hpp:58-85: dx_i = L_i * 2^(Depth-level) / 2^Depth / cells_i with
+    // cells_i = data_sizes[rank-1-i]
+    const int R = p->lay.rank;
+    for (int lvl = 0; lvl <= kMaxLevel; ++lvl)
+        for (int i = 0; i < 3; ++i)
+        {
+            if (i >= R || lvl > p->lay.depth)
+            {
+                p->dx[lvl][i] = 1.0;
+                continue;
+            }
+            const double pm    = (double)(1u << (p->lay.depth - lvl));
+            const double patch = p->lengths[i] * pm / (double)(1u << p->lay.depth);
+            p->dx[lvl][i]      = patch / (double)p->lay.size[R - 1 - i];
+        }
+}
+
+amrb_status ensure_scalars(amrb_pool* p, size_t steps)
+{
+    if (p->scal_cap >= steps + 2) return AMRB_OK;
+    // the carried dt-min of the previous batch lives in the old array: drop it
+    p->carry_valid = false;
+    if (p->d_dtmin) cudaFree(p->d_dtmin);
+    if (p->d_remaining) cudaFree(p->d_remaining);
+    if (p->d_dts) cudaFree(p->d_dts);
+    if (p->h_dts) cudaFreeHost(p->h_dts);
+    const size_t cap = std::max<size_t>(steps + 2, 64);
+    AMRB_CUDA(cudaMalloc(&p->d_dtmin, cap * sizeof(unsigned long long)));
+    AMRB_CUDA(cudaMalloc(&p->d_remaining, cap * sizeof(double)));
+    AMRB_CUDA(cudaMalloc(&p->d_dts, cap * sizeof(double)));
+    AMRB_CUDA(cudaHostAlloc(&p->h_dts, cap * sizeof(double), cudaHostAllocDefault));
+    p->scal_cap = cap;
+    return AMRB_OK;
+}
+
+amrb_status ensure_stage(amrb_pool* p, size_t doubles)
+{
+    if (p->stage_cap >= doubles) return AMRB_OK;
+    if (p->d_stage) cudaFree(p->d_stage);
+    p->stage_cap = 0;
+    AMRB_CUDA(cudaMalloc(&p->d_stage, doubles * sizeof(double)));
+    p->stage_cap = doubles;
+    return AMRB_OK;
+}
+
+void fill_step_args(const amrb_pool* p, StepArgs& a)
+{
+    a.cur       = p->cur;
+    a.nxt       = p->nxt;
+    a.nbr       = p->d_nbr;
+    a.meta      = p->d_meta;
+    a.level     = p->d_level;
+    a.list      = nullptr;
+    a.n_patches = (int)p->n_owned;
+    a.lazy_halo = (p->mode == 0) ? 1 : 0;
+    a.gamma     = p->gamma;
+    std::memcpy(a.dx, p->dx, sizeof(a.dx));
+    a.sc = StepScalars{ nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, p->cfl };
+}
+
+amrb_status check_launch(amrb_pool* p, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    ++p->launches;
+    return AMRB_OK;
+}
+
+amrb_status need_topology(const amrb_pool* p)
+{
+    if (!p->d_nbr || p->n_owned == 0) return fail(AMRB_ERR_STATE, "pool has no topology yet");
+    return AMRB_OK;
+}
+
+void swap_buffers(amrb_pool* p) { std::swap(p->cur, p->nxt); } // ndtree.hpp:1558-1579
+
+amrb_status pool_alloc_common(const amrb_layout* layout, size_t capacity, int device,
+                              amrb_pool** out)
+{
+    if (!layout || !out || capacity == 0) return fail(AMRB_ERR_ARGUMENT, "null layout/out or zero capacity");
+    const Ops* ops = find_ops(*layout);
+    if (!ops) return fail(AMRB_ERR_UNSUPPORTED, "no kernels instantiated for this patch shape / equation");
+    if (layout->depth < 1 || layout->depth > kMaxLevel) return fail(AMRB_ERR_ARGUMENT, "depth out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return fail(AMRB_ERR_CUDA, "no CUDA device: the hot path has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(AMRB_ERR_ARGUMENT, "bad device ordinal");
+    AMRB_CUDA(cudaSetDevice(device));
+    AMRB_CUDA(ops->prepare());
+    amrb_pool* p = new amrb_pool();
+    p->lay       = *layout;
+    p->ops       = ops;
+    p->device    = device;
+    p->capacity  = capacity;
+    p->flat      = amrb_layout_flat_size(layout);
+    p->data      = amrb_layout_data_size(layout);
+    compute_dx(p);
+    *out = p;
+    return AMRB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* amrb_last_error(void) { return g_error.c_str(); }
+const char* amrb_version(void) { return "gpuamr_b200 0.1 (sm_100a)"; }
+int         amrb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------ memory & sync
+amrb_status amrb_device_malloc(void** out, size_t bytes)
+{
+    if (!out) return fail(AMRB_ERR_ARGUMENT, "null out");
+    AMRB_CUDA(cudaMalloc(out, bytes));
+    return AMRB_OK;
+}
+amrb_status amrb_device_free(void* ptr)
+{
+    AMRB_CUDA(cudaFree(ptr));
+    return AMRB_OK;
+}
+amrb_status amrb_host_pinned_malloc(void** out, size_t bytes)
+{
+    if (!out) return fail(AMRB_ERR_ARGUMENT, "null out");
+    AMRB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return AMRB_OK;
+}
+amrb_status amrb_host_pinned_free(void* ptr)
+{
+    AMRB_CUDA(cudaFreeHost(ptr));
+    return AMRB_OK;
+}
+amrb_status amrb_copy_host_to_device(void* dst, const void* src, size_t bytes)
+{
+    AMRB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return AMRB_OK;
+}
+amrb_status amrb_copy_host_to_device_async(void* dst, const void* src, size_t bytes, void* stream)
+{
+    AMRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return AMRB_OK;
+}
+amrb_status amrb_copy_device_to_host(void* dst, const void* src, size_t bytes)
+{
+    AMRB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return AMRB_OK;
+}
+amrb_status amrb_copy_device_to_host_async(void* dst, const void* src, size_t bytes, void* stream)
+{
+    AMRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return AMRB_OK;
+}
+amrb_status amrb_copy_device_to_device(void* dst, const void* src, size_t bytes)
+{
+    AMRB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    return AMRB_OK;
+}
+amrb_status amrb_stream_create(void** out)
+{
+    if (!out) return fail(AMRB_ERR_ARGUMENT, "null out");
+    cudaStream_t s;
+    AMRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = s;
+    return AMRB_OK;
+}
+amrb_status amrb_stream_destroy(void* stream)
+{
+    AMRB_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return AMRB_OK;
+}
+amrb_status amrb_stream_synchronize(void* stream)
+{
+    AMRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return AMRB_OK;
+}
+amrb_status amrb_stream_wait_fence(void* stream, void* fence)
+{
+    AMRB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)fence, 0));
+    return AMRB_OK;
+}
+amrb_status amrb_fence_create(void** out)
+{
+    if (!out) return fail(AMRB_ERR_ARGUMENT, "null out");
+    cudaEvent_t e;
+    AMRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = e;
+    return AMRB_OK;
+}
+amrb_status amrb_fence_destroy(void* fence)
+{
+    AMRB_CUDA(cudaEventDestroy((cudaEvent_t)fence));
+    return AMRB_OK;
+}
+amrb_status amrb_fence_record(void* fence, void* stream)
+{
+    AMRB_CUDA(cudaEventRecord((cudaEvent_t)fence, (cudaStream_t)stream));
+    return AMRB_OK;
+}
+amrb_status amrb_fence_wait(void* fence)
+{
+    AMRB_CUDA(cudaEventSynchronize((cudaEvent_t)fence));
+    return AMRB_OK;
+}
+amrb_status amrb_device_synchronize(void)
+{
+    AMRB_CUDA(cudaDeviceSynchronize());
+    return AMRB_OK;
+}
+
+// ------------------------------------------------------------------------------ layout
+int amrb_layout_supported(const amrb_layout* layout) { return layout && find_ops(*layout) ? 1 : 0; }
+size_t amrb_layout_flat_size(const amrb_layout* l)
+{
+    size_t n = 1;
+    for (int k = 0; k < l->rank; ++k) n *= (size_t)(l->size[k] + 2 * l->halo);
+    return n;
+}
+size_t amrb_layout_data_size(const amrb_layout* l)
+{
+    size_t n = 1;
+    for (int k = 0; k < l->rank; ++k) n *= (size_t)l->size[k];
+    return n;
+}
+
+// ------------------------------------------------------------------------------ pool lifetime
+amrb_status amrb_pool_create(const amrb_layout* layout, size_t capacity, int device,
+                             amrb_pool** out)
+{
+    AMRB_TRY(pool_alloc_common(layout, capacity, device, out));
+    amrb_pool* p = *out;
+    p->own_mem   = true;
+    const size_t bytes = capacity * p->flat * sizeof(double);
+    for (int f = 0; f < layout->nvar; ++f)
+    {
+        // zero-initialised: corner ghosts are observable
+        if (cudaMalloc(&p->cur.p[f], bytes) != cudaSuccess ||
+            cudaMalloc(&p->nxt.p[f], bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            amrb_pool_destroy(p);
+            *out = nullptr;
+            return fail(AMRB_ERR_CUDA, "cudaMalloc of the patch pool failed");
+        }
+        cudaMemset(p->cur.p[f], 0, bytes);
+        cudaMemset(p->nxt.p[f], 0, bytes);
+    }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        amrb_pool_destroy(p);
+        *out = nullptr;
+        return fail(AMRB_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    p->own_stream = true;
+    AMRB_CUDA(cudaEventCreateWithFlags(&p->batch_done, cudaEventDisableTiming));
+    AMRB_CUDA(cudaDeviceSynchronize());
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_create_external(const amrb_layout* layout, size_t capacity, int device,
+                                      double* const* cur, double* const* nxt, void* stream,
+                                      amrb_pool** out)
+{
+    if (!cur || !nxt) return fail(AMRB_ERR_ARGUMENT, "null field pointer arrays");
+    for (int f = 0; layout && f < layout->nvar && f < kMaxVar; ++f)
+        if (!cur[f] || !nxt[f] || ((uintptr_t)cur[f] & 15) || ((uintptr_t)nxt[f] & 15))
+            return fail(AMRB_ERR_ARGUMENT, "field pointers must be non-null and 16-byte aligned");
+    AMRB_TRY(pool_alloc_common(layout, capacity, device, out));
+    amrb_pool* p = *out;
+    for (int f = 0; f < layout->nvar; ++f)
+    {
+        p->cur.p[f] = cur[f];
+        p->nxt.p[f] = nxt[f];
+    }
+    p->stream = (cudaStream_t)stream;
+    AMRB_CUDA(cudaEventCreateWithFlags(&p->batch_done, cudaEventDisableTiming));
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_destroy(amrb_pool* p)
+{
+    if (!p) return AMRB_OK;
+    cudaSetDevice(p->device);
+    if (p->stream || !p->own_stream) cudaStreamSynchronize(p->stream);
+    if (p->own_mem)
+        for (int f = 0; f < kMaxVar; ++f)
+        {
+            if (p->cur.p[f]) cudaFree(p->cur.p[f]);
+            if (p->nxt.p[f]) cudaFree(p->nxt.p[f]);
+        }
+    cudaFree(p->d_nbr);
+    cudaFree(p->d_meta);
+    cudaFree(p->d_level);
+    cudaFree(p->d_dtmin);
+    cudaFree(p->d_remaining);
+    cudaFree(p->d_dts);
+    cudaFree(p->d_stage);
+    cudaFree(p->d_flags);
+    cudaFree(p->d_plan);
+    if (p->h_dts) cudaFreeHost(p->h_dts);
+    if (p->batch_done) cudaEventDestroy(p->batch_done);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    cudaGetLastError();
+    delete p;
+    return AMRB_OK;
+}
+
+size_t  amrb_pool_capacity(const amrb_pool* p) { return p ? p->capacity : 0; }
+size_t  amrb_pool_size(const amrb_pool* p) { return p ? p->n_owned : 0; }
+void*   amrb_pool_stream(const amrb_pool* p) { return p ? (void*)p->stream : nullptr; }
+double* amrb_pool_field(const amrb_pool* p, int f)
+{
+    return (p && f >= 0 && f < p->lay.nvar) ? p->cur.p[f] : nullptr;
+}
+double* amrb_pool_next_field(const amrb_pool* p, int f)
+{
+    return (p && f >= 0 && f < p->lay.nvar) ? p->nxt.p[f] : nullptr;
+}
+uint64_t amrb_pool_launch_count(const amrb_pool* p) { return p ? p->launches : 0; }
+
+amrb_status amrb_pool_set_mode(amrb_pool* p, int mode)
+{
+    if (!p || (mode != 0 && mode != 1)) return fail(AMRB_ERR_ARGUMENT, "mode must be 0 or 1");
+    p->mode = mode;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_set_physics(amrb_pool* p, const double* lengths, double gamma, double cfl)
+{
+    if (!p || !lengths) return fail(AMRB_ERR_ARGUMENT, "null pool/lengths");
+    for (int i = 0; i < p->lay.rank; ++i) p->lengths[i] = lengths[i];
+    p->gamma = gamma;
+    p->cfl   = cfl;
+    compute_dx(p);
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+
+// ------------------------------------------------------------------------------ topology upload
+amrb_status amrb_pool_set_topology(amrb_pool* p, size_t n_owned, size_t n_total,
+                                   const int32_t* levels, const int8_t* rel, const int32_t* nbr,
+                                   const int8_t* quad)
+{
+    if (!p || !levels || !rel || !nbr || !quad) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (n_owned == 0 || n_total < n_owned) return fail(AMRB_ERR_ARGUMENT, "bad patch counts");
+    if (n_total > p->capacity) return fail(AMRB_ERR_CAPACITY, "patch count exceeds pool capacity");
+    AMRB_TRY(set_device(p));
+    const int R = p->lay.rank, ND = 2 * R, KF = 1 << (R - 1);
+    // compact device form: int32 nbr[P][ND][KF]; uint8 meta[P][ND] = rel | quadrant bits << 2
+    std::vector<uint8_t> meta(n_owned * ND);
+    for (size_t i = 0; i < n_owned * ND; ++i)
+    {
+        const int r = rel[i];
+        if (r < 0 || r > 3) return fail(AMRB_ERR_ARGUMENT, "relation out of range");
+        int m = r;
+        if (r == AMRB_REL_COARSER)
+            for (int k = 0; k < R; ++k) m |= (quad[i * R + k] & 1) << (2 + k);
+        meta[i] = (uint8_t)m;
+        const int need = (r == AMRB_REL_FINER) ? KF : (r == AMRB_REL_NONE ? 0 : 1);
+        for (int k = 0; k < need; ++k)
+        {
+            const int32_t n = nbr[i * KF + k];
+            if (n < 0 || (size_t)n >= n_total)
+                return fail(AMRB_ERR_ARGUMENT, "neighbor index out of range");
+        }
+    }
+    for (size_t i = 0; i < n_owned; ++i)
+        if (levels[i] < 0 || levels[i] > p->lay.depth)
+            return fail(AMRB_ERR_ARGUMENT, "level out of range");
+    if (p->table_cap < n_owned)
+    {
+        cudaFree(p->d_nbr);
+        cudaFree(p->d_meta);
+        cudaFree(p->d_level);
+        p->d_nbr = nullptr;
+        p->d_meta = nullptr;
+        p->d_level = nullptr;
+        p->table_cap = 0;
+        const size_t cap = std::max(n_owned, std::min(p->capacity, n_owned * 2));
+        AMRB_CUDA(cudaMalloc(&p->d_nbr, cap * ND * KF * sizeof(int32_t)));
+        AMRB_CUDA(cudaMalloc(&p->d_meta, cap * ND));
+        AMRB_CUDA(cudaMalloc(&p->d_level, cap * sizeof(int32_t)));
+        p->table_cap = cap;
+    }
+    // the previous tables may still be in use by launches in flight
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    AMRB_CUDA(cudaMemcpy(p->d_nbr, nbr, n_owned * ND * KF * sizeof(int32_t), cudaMemcpyHostToDevice));
+    AMRB_CUDA(cudaMemcpy(p->d_meta, meta.data(), n_owned * ND, cudaMemcpyHostToDevice));
+    AMRB_CUDA(cudaMemcpy(p->d_level, levels, n_owned * sizeof(int32_t), cudaMemcpyHostToDevice));
+    p->n_owned     = n_owned;
+    p->n_total     = n_total;
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+
+// ------------------------------------------------------------------------------ host <-> device
+static amrb_status check_range(const amrb_pool* p, int field, size_t first, size_t n, const void* host)
+{
+    if (!p || !host) return fail(AMRB_ERR_ARGUMENT, "null pool/host");
+    if (field < 0 || field >= p->lay.nvar) return fail(AMRB_ERR_ARGUMENT, "field out of range");
+    if (first + n > p->capacity) return fail(AMRB_ERR_CAPACITY, "patch range exceeds capacity");
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_upload(amrb_pool* p, int field, size_t first, size_t n, const double* host)
+{
+    AMRB_TRY(check_range(p, field, first, n, host));
+    AMRB_TRY(set_device(p));
+    AMRB_CUDA(cudaMemcpyAsync(p->cur.p[field] + first * p->flat, host, n * p->flat * sizeof(double),
+                              cudaMemcpyHostToDevice, p->stream));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+amrb_status amrb_pool_download(amrb_pool* p, int field, size_t first, size_t n, double* host)
+{
+    AMRB_TRY(check_range(p, field, first, n, host));
+    AMRB_TRY(set_device(p));
+    AMRB_CUDA(cudaMemcpyAsync(host, p->cur.p[field] + first * p->flat, n * p->flat * sizeof(double),
+                              cudaMemcpyDeviceToHost, p->stream));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    return AMRB_OK;
+}
+amrb_status amrb_pool_upload_interior(amrb_pool* p, int field, size_t first, size_t n,
+                                      const double* host)
+{
+    AMRB_TRY(check_range(p, field, first, n, host));
+    AMRB_TRY(set_device(p));
+    if (n == 0) return AMRB_OK;
+    AMRB_TRY(ensure_stage(p, n * p->data));
+    AMRB_CUDA(cudaMemcpyAsync(p->d_stage, host, n * p->data * sizeof(double), cudaMemcpyHostToDevice,
+                              p->stream));
+    p->ops->interior(p->stream, p->cur.p[field] + first * p->flat, p->d_stage, (int)n, 1);
+    AMRB_TRY(check_launch(p, "interior_copy_kernel"));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+amrb_status amrb_pool_download_interior(amrb_pool* p, int field, size_t first, size_t n,
+                                        double* host)
+{
+    AMRB_TRY(check_range(p, field, first, n, host));
+    AMRB_TRY(set_device(p));
+    if (n == 0) return AMRB_OK;
+    AMRB_TRY(ensure_stage(p, n * p->data));
+    p->ops->interior(p->stream, p->cur.p[field] + first * p->flat, p->d_stage, (int)n, 0);
+    AMRB_TRY(check_launch(p, "interior_copy_kernel"));
+    AMRB_CUDA(cudaMemcpyAsync(host, p->d_stage, n * p->data * sizeof(double), cudaMemcpyDeviceToHost,
+                              p->stream));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    return AMRB_OK;
+}
+
+// ------------------------------------------------------------------------------ halo
+amrb_status amrb_pool_halo_exchange(amrb_pool* p)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
+    return check_launch(p, "halo_kernel");
+}
+
+// ------------------------------------------------------------------------------ stepping
+amrb_status amrb_pool_compute_dt(amrb_pool* p, double* dt_out)
+{
+    if (!p || !dt_out) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    if (p->batch_open || p->batch_pending) return fail(AMRB_ERR_STATE, "a batch is in flight");
+    AMRB_TRY(ensure_scalars(p, 1));
+    init_scalars_kernel<<<1, 32, 0, p->stream>>>(p->d_dtmin, 0, 1, nullptr, 0.0, nullptr);
+    AMRB_TRY(check_launch(p, "init_scalars_kernel"));
+    StepArgs a;
+    fill_step_args(p, a);
+    p->ops->compute_dt(p->stream, a, p->d_dtmin);
+    AMRB_TRY(check_launch(p, "compute_dt_kernel"));
+    double raw = 0.0;
+    AMRB_CUDA(cudaMemcpyAsync(&raw, p->d_dtmin, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    *dt_out        = p->cfl * raw; // amr_solver.hpp:412
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_step(amrb_pool* p, double dt)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is open");
+    if (p->mode == 1)
+    {
+        p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
+        AMRB_TRY(check_launch(p, "halo_kernel"));
+    }
+    StepArgs a;
+    fill_step_args(p, a);
+    a.sc.fixed_dt = dt;
+    p->ops->step(p->stream, a, (int)p->n_owned);
+    AMRB_TRY(check_launch(p, "step_kernel"));
+    swap_buffers(p);
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_batch_begin(amrb_pool* p, size_t max_steps, double remaining)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is already open");
+    if (p->batch_pending)
+    {
+        // same as wait_for_pending_dt_copy() at the top of advance_batch_async (amr_solver.hpp:163)
+        AMRB_CUDA(cudaEventSynchronize(p->batch_done));
+        p->batch_pending = false;
+    }
+    const size_t last = p->batch_steps; // slot holding the dt-min of the state we start from
+    const bool   carry = p->carry_valid && p->scal_cap >= max_steps + 2;
+    if (carry && last != 0)
+        AMRB_CUDA(cudaMemcpyAsync(p->d_dtmin, p->d_dtmin + last, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToDevice, p->stream));
+    AMRB_TRY(ensure_scalars(p, max_steps));
+    const int first = carry ? 1 : 0;
+    const int count = (int)max_steps + 1 - first;
+    init_scalars_kernel<<<(count + 255) / 256 + 1, 256, 0, p->stream>>>(
+        p->d_dtmin, first, count, p->d_remaining, remaining, p->d_dts);
+    AMRB_TRY(check_launch(p, "init_scalars_kernel"));
+    if (!carry)
+    {
+        StepArgs a;
+        fill_step_args(p, a);
+        p->ops->compute_dt(p->stream, a, p->d_dtmin);
+        AMRB_TRY(check_launch(p, "compute_dt_kernel"));
+    }
+    p->batch_steps  = max_steps;
+    p->batch_k      = 0;
+    p->batch_open   = true;
+    p->step_touched = false;
+    p->carry_valid  = false;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_step_partial(amrb_pool* p, const int32_t* dev_list, size_t count)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (!p->batch_open) return fail(AMRB_ERR_STATE, "no open batch");
+    if (p->batch_k >= p->batch_steps) return fail(AMRB_ERR_STATE, "batch step budget exhausted");
+    AMRB_TRY(set_device(p));
+    const size_t k = p->batch_k;
+    if (p->mode == 1 && !p->step_touched)
+    {
+        p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
+        AMRB_TRY(check_launch(p, "halo_kernel"));
+    }
+    StepArgs a;
+    fill_step_args(p, a);
+    a.list = dev_list;
+    a.sc   = StepScalars{ p->d_dtmin + k,         p->d_dtmin + k + 1, p->d_remaining + k,
+                          p->d_remaining + k + 1, p->d_dts + k,       0.0,
+                          p->cfl };
+    const int n_items = dev_list ? (int)count : (int)p->n_owned;
+    if (n_items > 0)
+    {
+        p->ops->step(p->stream, a, n_items);
+        AMRB_TRY(check_launch(p, "step_kernel"));
+    }
+    p->step_touched = true;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_step_commit(amrb_pool* p)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (!p->batch_open || !p->step_touched) return fail(AMRB_ERR_STATE, "no step to commit");
+    swap_buffers(p);
+    ++p->batch_k;
+    p->step_touched = false;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_batch_end(amrb_pool* p, int materialise_halos)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (!p->batch_open || p->step_touched) return fail(AMRB_ERR_STATE, "batch not open or step uncommitted");
+    AMRB_TRY(set_device(p));
+    if (materialise_halos)
+    {
+        // post-condition of every reference step: face halos of the current buffer are filled
+        // (amr_solver.hpp:351-352)
+        p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
+        AMRB_TRY(check_launch(p, "halo_kernel"));
+    }
+    p->batch_steps = p->batch_k; // slot index of the dt-min of the final state
+    if (p->batch_k > 0)
+        AMRB_CUDA(cudaMemcpyAsync(p->h_dts, p->d_dts, p->batch_k * sizeof(double),
+                                  cudaMemcpyDeviceToHost, p->stream));
+    AMRB_CUDA(cudaEventRecord(p->batch_done, p->stream));
+    p->batch_open    = false;
+    p->batch_pending = true;
+    p->carry_valid   = true;
+    return AMRB_OK;
+}
+
+double* amrb_pool_dtmin_slot(amrb_pool* p, size_t k)
+{
+    if (!p || !p->d_dtmin || k + 1 > p->scal_cap) return nullptr;
+    return reinterpret_cast<double*>(p->d_dtmin + k);
+}
+
+amrb_status amrb_pool_advance_batch_async(amrb_pool* p, size_t steps, double remaining)
+{
+    AMRB_TRY(amrb_pool_batch_begin(p, steps, remaining));
+    for (size_t k = 0; k < steps; ++k)
+    {
+        AMRB_TRY(amrb_pool_step_partial(p, nullptr, 0));
+        AMRB_TRY(amrb_pool_step_commit(p));
+    }
+    return amrb_pool_batch_end(p, 1);
+}
+
+amrb_status amrb_pool_finish_advance_batch(amrb_pool* p, double* dt_sum, size_t* executed,
+                                           double* dts, size_t dts_capacity)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "batch still open");
+    double sum = 0.0;
+    size_t cnt = 0;
+    if (p->batch_pending)
+    {
+        AMRB_TRY(set_device(p));
+        AMRB_CUDA(cudaEventSynchronize(p->batch_done));
+        p->batch_pending = false;
+    }
+    // accumulate exactly like finalize_step_dt_kernel: acc += step_dt in step order, count the
+    // steps with dt > 0 (src/cuda/fvm_time_step.cu:224-230)
+    for (size_t k = 0; k < p->batch_k; ++k)
+    {
+        const double d = p->h_dts[k];
+        sum += d;
+        if (d > 0.0)
+        {
+            if (dts && cnt < dts_capacity) dts[cnt] = d;
+            ++cnt;
+        }
+    }
+    if (dt_sum) *dt_sum = sum;
+    if (executed) *executed = cnt;
+    return AMRB_OK;
+}
+
+// ------------------------------------------------------------------------------ ghost faces
+size_t amrb_pool_face_slab_doubles(const amrb_pool* p, int direction)
+{
+    if (!p || direction < 0 || direction >= 2 * p->lay.rank) return 0;
+    size_t n = (size_t)p->lay.halo;
+    for (int k = 1; k < p->lay.rank; ++k) n *= (size_t)p->lay.size[0];
+    return n;
+}
+
+static amrb_status faces(amrb_pool* p, const int32_t* entries, size_t count, double* buffer, int unpack)
+{
+    if (!p || (count && (!entries || !buffer))) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (count == 0) return AMRB_OK;
+    AMRB_TRY(set_device(p));
+    p->ops->faces(p->stream, p->cur, entries, (int)count, buffer, unpack);
+    return check_launch(p, "face_pack_kernel");
+}
+amrb_status amrb_pool_pack_faces(amrb_pool* p, const int32_t* e, size_t n, double* b)
+{
+    return faces(p, e, n, b, 0);
+}
+amrb_status amrb_pool_unpack_faces(amrb_pool* p, const int32_t* e, size_t n, const double* b)
+{
+    return faces(p, e, n, const_cast<double*>(b), 1);
+}
+
+// ------------------------------------------------------------------------------ reconstruct
+amrb_status amrb_pool_apply_plan(amrb_pool* p, size_t new_size, const int8_t* kind,
+                                 const int32_t* src, const int8_t* child)
+{
+    if (!p || !kind || !src || !child) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (new_size == 0 || new_size > p->capacity) return fail(AMRB_ERR_CAPACITY, "new size exceeds capacity");
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is open");
+    AMRB_TRY(set_device(p));
+    const size_t bytes = new_size * (sizeof(int8_t) * 2 + sizeof(int32_t));
+    if (p->plan_cap < bytes)
+    {
+        cudaFree(p->d_plan);
+        p->plan_cap = 0;
+        AMRB_CUDA(cudaMalloc(&p->d_plan, bytes * 2));
+        p->plan_cap = bytes * 2;
+    }
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    int32_t* d_src   = static_cast<int32_t*>(p->d_plan);
+    int8_t*  d_kind  = reinterpret_cast<int8_t*>(d_src + new_size);
+    int8_t*  d_child = d_kind + new_size;
+    AMRB_CUDA(cudaMemcpy(d_src, src, new_size * sizeof(int32_t), cudaMemcpyHostToDevice));
+    AMRB_CUDA(cudaMemcpy(d_kind, kind, new_size, cudaMemcpyHostToDevice));
+    AMRB_CUDA(cudaMemcpy(d_child, child, new_size, cudaMemcpyHostToDevice));
+    p->ops->plan(p->stream, p->cur, p->nxt, d_kind, d_src, d_child, (int)new_size);
+    AMRB_TRY(check_launch(p, "plan_kernel"));
+    swap_buffers(p);
+    p->carry_valid = false;
+    // tables are stale until the caller uploads the new topology
+    p->n_owned = 0;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_patch_max_flags(amrb_pool* p, int field, double refine_threshold,
+                                      double coarsen_threshold, int min_level, int max_level,
+                                      int8_t* flags)
+{
+    if (!p || !flags) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (field < 0 || field >= p->lay.nvar) return fail(AMRB_ERR_ARGUMENT, "field out of range");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    if (p->flags_cap < p->n_owned)
+    {
+        cudaFree(p->d_flags);
+        p->flags_cap = 0;
+        AMRB_CUDA(cudaMalloc(&p->d_flags, p->n_owned * 2));
+        p->flags_cap = p->n_owned * 2;
+    }
+    p->ops->flags(p->stream, p->cur.p[field], p->d_level, (int)p->n_owned, refine_threshold,
+                  coarsen_threshold, min_level, max_level, p->d_flags);
+    AMRB_TRY(check_launch(p, "patch_max_flags_kernel"));
+    AMRB_CUDA(cudaMemcpyAsync(flags, p->d_flags, p->n_owned, cudaMemcpyDeviceToHost, p->stream));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    return AMRB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,248 @@
+/* gpuamr_b200.h — C ABI of the B200-native gpu-amr hot path.
+ *
+ * Everything the host side (C++ templates in include/ndtree, include/solver; the ctypes
+ * harness in gpu-amr_b200/binding.py) needs from the GPU goes through these entry points:
+ * plain pointers, sizes and POD structs, no C++ or torch types.  Each group cites the
+ * reference interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns amrb_status (0 = AMRB_OK); amrb_last_error() gives the text of
+ *     the last failure on the calling thread.  The reference throws std::runtime_error across
+ *     this boundary (src/cuda/halo_exchange.cu:16-26) or silently drops launch errors
+ *     (src/cuda/fvm_time_step.cu:142,238,244,261,282); the inline C++ shim re-throws.
+ *   - all launches are asynchronous on the pool's stream unless stated otherwise.
+ *   - patches are padded row-major tensors, last layout dim fastest, every dim padded by
+ *     2*halo (containers/static_layout.hpp:28-37, ndtree/patch_layout.hpp:14-116); field f of
+ *     patch p lives at field_base[f] + p*flat_size (ndtree.hpp:166-174).
+ *   - directions: d = 2*layout_dim + (positive ? 1 : 0)  (ndtree/neighbor.hpp:103-255).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GPUAMR_B200_H
+#define GPUAMR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int amrb_status;
+enum {
+    AMRB_OK            = 0,
+    AMRB_ERR_ARGUMENT  = 1,
+    AMRB_ERR_CUDA      = 2,
+    AMRB_ERR_CAPACITY  = 3,
+    AMRB_ERR_UNSUPPORTED = 4, /* shape/equation combination not instantiated */
+    AMRB_ERR_STATE     = 5
+};
+
+enum { AMRB_EQ_ADVECTION = 0, AMRB_EQ_EULER = 1 };             /* solver/{Advection,Euler}Physics.hpp */
+enum { AMRB_REL_NONE = 0, AMRB_REL_SAME = 1, AMRB_REL_FINER = 2, AMRB_REL_COARSER = 3 };
+                                                                /* cuda/halo_exchange.hpp:11-17 */
+enum { AMRB_STABLE = 0, AMRB_REFINE = 1, AMRB_COARSEN = 2 };   /* ndtree.hpp:265-270 refine_status_t */
+
+const char* amrb_last_error(void);
+const char* amrb_version(void);
+/* number of visible CUDA devices (0 on a CPU-only box); never fails */
+int amrb_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. memory & sync — replaces amr::cuda::device_malloc … async_copy_fence_wait
+ *    (include/cuda/device_buffer.hpp:9-48, src/cuda/device_buffer.cu:31-239)
+ * ---------------------------------------------------------------------------------------- */
+amrb_status amrb_device_malloc(void** out, size_t bytes);
+amrb_status amrb_device_free(void* ptr);
+amrb_status amrb_host_pinned_malloc(void** out, size_t bytes);
+amrb_status amrb_host_pinned_free(void* ptr);
+amrb_status amrb_copy_host_to_device(void* dst, const void* src, size_t bytes);
+amrb_status amrb_copy_host_to_device_async(void* dst, const void* src, size_t bytes, void* stream);
+amrb_status amrb_copy_device_to_host(void* dst, const void* src, size_t bytes);
+amrb_status amrb_copy_device_to_host_async(void* dst, const void* src, size_t bytes, void* stream);
+amrb_status amrb_copy_device_to_device(void* dst, const void* src, size_t bytes);
+amrb_status amrb_stream_create(void** out);          /* async_copy_stream_create  */
+amrb_status amrb_stream_destroy(void* stream);
+amrb_status amrb_stream_synchronize(void* stream);
+amrb_status amrb_stream_wait_fence(void* stream, void* fence);
+amrb_status amrb_fence_create(void** out);           /* async_copy_fence_create   */
+amrb_status amrb_fence_destroy(void* fence);
+amrb_status amrb_fence_record(void* fence, void* stream);
+amrb_status amrb_fence_wait(void* fence);
+amrb_status amrb_device_synchronize(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. patch layout (ndtree/patch_layout.hpp:14-116, containers/container_utils.hpp:56-64)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct amrb_layout
+{
+    int32_t rank;      /* 2 | 3 */
+    int32_t size[3];   /* interior cells per layout dim, dim 0 slowest; unused = 1 */
+    int32_t halo;      /* ghost width per side (1 | 2) */
+    int32_t nvar;      /* fields per cell: 1 (advection) or rank+2 (Euler) */
+    int32_t equation;  /* AMRB_EQ_* */
+    int32_t depth;     /* morton_id<Depth,Rank>: finest level */
+} amrb_layout;
+
+/* 1 if fused kernels for this shape were compiled into the library */
+int    amrb_layout_supported(const amrb_layout* layout);
+size_t amrb_layout_flat_size(const amrb_layout* layout); /* prod(size+2*halo) */
+size_t amrb_layout_data_size(const amrb_layout* layout); /* prod(size)        */
+
+/* ------------------------------------------------------------------------------------------
+ * 3. device patch pool — replaces ndtree's m_data_buffers / m_next_buffers device mirrors,
+ *    halo metadata and level buffers (ndtree.hpp:341-409, 561-679, 1606-1700, 2004-2060)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct amrb_pool amrb_pool;
+
+/* device-resident SoA pool of `capacity` patches, current + next buffer per field,
+ * zero-initialised (corner ghosts are observable by max criteria). */
+amrb_status amrb_pool_create(const amrb_layout* layout, size_t capacity, int device,
+                             amrb_pool** out);
+/* same, over caller-owned device memory (e.g. torch tensors): cur[f], nxt[f] hold
+ * capacity*flat_size doubles each; stream may be NULL (legacy default stream). */
+amrb_status amrb_pool_create_external(const amrb_layout* layout, size_t capacity, int device,
+                                      double* const* cur, double* const* nxt, void* stream,
+                                      amrb_pool** out);
+amrb_status amrb_pool_destroy(amrb_pool* pool);
+size_t      amrb_pool_capacity(const amrb_pool* pool);
+size_t      amrb_pool_size(const amrb_pool* pool);
+void*       amrb_pool_stream(const amrb_pool* pool);
+/* current-buffer device pointer of field f (ndtree::get_device_buffer, ndtree.hpp:561-581) */
+double*     amrb_pool_field(const amrb_pool* pool, int field);
+double*     amrb_pool_next_field(const amrb_pool* pool, int field);
+
+/* neighbor / halo index tables in the reference's host form, one row per (patch, direction):
+ *   levels[P]; rel[P][2R]; nbr[P][2R][2^(R-1)] (linear patch index, -1 padded);
+ *   quad[P][2R][R] contact quadrant of a coarser neighbor (ndtree/neighbor.hpp:22-100,
+ *   cuda/halo_exchange.hpp:19-26, ndtree.hpp:1606-1660 rebuild_halo_exchange_metadata).
+ * n_total >= n_owned: slots [n_owned, n_total) are ghost slots (copies of patches owned by
+ * another GPU) that are only ever read as halo sources.  Converts to the compact device
+ * format and uploads; call once after every refine/coarsen. */
+amrb_status amrb_pool_set_topology(amrb_pool* pool, size_t n_owned, size_t n_total,
+                                   const int32_t* levels, const int8_t* rel, const int32_t* nbr,
+                                   const int8_t* quad);
+/* physical domain lengths per *physical* axis (x,y,z) and solver constants
+ * (solver/physics_system.hpp:58-85, amr_solver.hpp:62-69) */
+amrb_status amrb_pool_set_physics(amrb_pool* pool, const double* lengths, double gamma,
+                                  double cfl);
+
+/* bulk host<->device transfer of whole padded patches of the CURRENT buffer
+ * (ndtree::sync_current_{to,from}_device, ndtree.hpp:583-640); blocking */
+amrb_status amrb_pool_upload(amrb_pool* pool, int field, size_t first_patch, size_t n_patches,
+                             const double* host);
+amrb_status amrb_pool_download(amrb_pool* pool, int field, size_t first_patch, size_t n_patches,
+                               double* host);
+/* interior-only variants (host array is [n_patches][prod(size)]) */
+amrb_status amrb_pool_upload_interior(amrb_pool* pool, int field, size_t first_patch,
+                                      size_t n_patches, const double* host);
+amrb_status amrb_pool_download_interior(amrb_pool* pool, int field, size_t first_patch,
+                                        size_t n_patches, double* host);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. halo fill — replaces halo_exchange_scalar_patches_inplace, one launch per field
+ *    (include/cuda/halo_exchange.hpp:42-47, src/cuda/halo_exchange.cu:291-370) and the CPU
+ *    operators same_t / finer_t / coarser_t (ndtree/patch_utils.hpp:303-441).
+ *    One launch materialises the face halos of ALL fields of the current buffer, in place.
+ * ---------------------------------------------------------------------------------------- */
+amrb_status amrb_pool_halo_exchange(amrb_pool* pool);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. time stepping — replaces launch_compute_dt_kernel_device, launch_finalize_step_dt,
+ *    launch_time_step_kernel_with_device_dt, launch_set_{double,uint32}_buffer
+ *    (include/cuda/fvm_time_step.hpp:10-58) and the loop in
+ *    amr_solver::advance_batch_async / finish_advance_batch (solver/amr_solver.hpp:155-262).
+ * ---------------------------------------------------------------------------------------- */
+/* cfl * min dx/speed over the current buffer (amr_solver.hpp:355-413); blocking */
+amrb_status amrb_pool_compute_dt(amrb_pool* pool, double* dt_out);
+/* one explicit step with a host-provided dt: fused halo gather + flux + update into the
+ * next buffer, then swap (amr_solver::time_step_cpu, amr_solver.hpp:265-353).  Global face
+ * halos of the new current buffer are NOT materialised (call amrb_pool_halo_exchange). */
+amrb_status amrb_pool_step(amrb_pool* pool, double dt);
+/* up to `steps` steps with device-resident dt / remaining-time / step-count scalars, each
+ * step one fused launch (halo gather + flux + update + next-dt reduction).  After the last
+ * step face halos are materialised, so the post-condition of the reference holds:
+ * current buffers hold the new state with face halos filled.  Asynchronous. */
+amrb_status amrb_pool_advance_batch_async(amrb_pool* pool, size_t steps, double remaining_time);
+/* waits for the batch; returns sum of step dts, number of executed (dt > 0) steps and,
+ * if dts != NULL, the first min(executed, dts_capacity) individual step sizes */
+amrb_status amrb_pool_finish_advance_batch(amrb_pool* pool, double* dt_sum, size_t* executed,
+                                           double* dts, size_t dts_capacity);
+/* statistics for bench accounting: kernels launched by this pool since creation */
+uint64_t amrb_pool_launch_count(const amrb_pool* pool);
+/* select the step implementation: 0 = fused lazy-halo kernel (default),
+ * 1 = unfused (materialise halos every step, then stencil) — kept for A/B measurement */
+amrb_status amrb_pool_set_mode(amrb_pool* pool, int mode);
+
+/* the same batch, decomposed so that a multi-GPU driver can interleave ghost-face traffic:
+ *   batch_begin(max_steps, remaining)
+ *   per step: step_partial(list A) ... step_partial(list B); [all-reduce(min) of dtmin_slot(k+1)];
+ *             step_commit()                      (swap buffers, k -> k+1)
+ *   batch_end()                                  (materialise halos, start the scalar read-back)
+ * dev_list = device array of owned patch indices (NULL = all owned patches).  Every partial
+ * launch of step k reads the same dt scalars and min-reduces into slot k+1. */
+amrb_status amrb_pool_batch_begin(amrb_pool* pool, size_t max_steps, double remaining_time);
+amrb_status amrb_pool_step_partial(amrb_pool* pool, const int32_t* dev_list, size_t count);
+amrb_status amrb_pool_step_commit(amrb_pool* pool);
+amrb_status amrb_pool_batch_end(amrb_pool* pool, int materialise_halos);
+/* device address of the dt-min slot entering step k of the current batch (a positive double;
+ * min across GPUs = all-reduce(min) on it as float64) */
+double*     amrb_pool_dtmin_slot(amrb_pool* pool, size_t k);
+
+/* ------------------------------------------------------------------------------------------
+ * 6. inter-GPU ghost faces (no reference counterpart: the reference is single-GPU).
+ *    pack: gathers, for each (patch, direction) entry, the h-thick interior slab next to that
+ *    face of every field into a contiguous send buffer; unpack: scatters a received buffer
+ *    into the same slab of a ghost slot.  Entry = {int32 patch, int32 direction}.
+ * ---------------------------------------------------------------------------------------- */
+size_t      amrb_pool_face_slab_doubles(const amrb_pool* pool, int direction); /* per field */
+amrb_status amrb_pool_pack_faces(amrb_pool* pool, const int32_t* dev_entries, size_t count,
+                                 double* dev_buffer);
+amrb_status amrb_pool_unpack_faces(amrb_pool* pool, const int32_t* dev_entries, size_t count,
+                                   const double* dev_buffer);
+
+/* ------------------------------------------------------------------------------------------
+ * 7. host topology — Morton-ordered leaf set, refine/coarsen with 2:1 balancing and the
+ *    neighbor tables derived from it.  Replaces the host side of ndtree::reconstruct_tree
+ *    (ndtree.hpp:886-940, 1127-1271) and neighbor maintenance (ndtree/neighbor.hpp:291-572)
+ *    with a set-based formulation: tables depend only on the set of leaves.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct amrb_tree amrb_tree;
+
+amrb_status amrb_tree_create(int rank, int depth, amrb_tree** out); /* single periodic root */
+amrb_status amrb_tree_destroy(amrb_tree* tree);
+size_t      amrb_tree_size(const amrb_tree* tree);
+const uint64_t* amrb_tree_ids(const amrb_tree* tree); /* ascending morton ids (<<6 | level) */
+/* one reconstruct pass. flags[i] in AMRB_{STABLE,REFINE,COARSEN} for leaf i.  On return
+ * `plan` (if not NULL, capacity >= new size) holds for each new leaf the transfer source:
+ * plan_kind[i] 0 = copy of old leaf plan_src[i]; 1 = prolongation from old leaf plan_src[i]
+ * (child number in plan_child[i]); 2 = restriction of old leaves plan_src[i] .. +2^rank-1.
+ * returns changed = 1 when the leaf set changed. */
+amrb_status amrb_tree_reconstruct(amrb_tree* tree, const int8_t* flags, size_t capacity,
+                                  int* changed);
+size_t      amrb_tree_plan_size(const amrb_tree* tree);
+amrb_status amrb_tree_plan(const amrb_tree* tree, int8_t* kind, int32_t* src, int8_t* child);
+/* neighbor tables of the current leaf set (same format as amrb_pool_set_topology) */
+amrb_status amrb_tree_tables(const amrb_tree* tree, int32_t* levels, int8_t* rel, int32_t* nbr,
+                             int8_t* quad);
+uint64_t amrb_morton_encode(int rank, const uint32_t* coords, int level);
+void     amrb_morton_decode(int rank, uint64_t id, uint32_t* coords, int* level);
+
+/* apply a reconstruct plan on the device: gathers the new current buffer from the old one
+ * (copy / prolongation / restriction fused with the Morton re-sort), replacing
+ * interpolate/restrict_scalar_patches_inplace + permute_patches_inplace_batch
+ * (include/cuda/intergrid_transfer.hpp:28-42, include/cuda/permutation.hpp:10-17). */
+amrb_status amrb_pool_apply_plan(amrb_pool* pool, size_t new_size, const int8_t* kind,
+                                 const int32_t* src, const int8_t* child);
+
+/* per-patch refinement decisions on the device: max over ALL flat cells of one field
+ * (benchmark criterion, src/cuda/fvm_refinement_criterion.cu:27-67):
+ * Refine if max > refine_threshold && level < max_level; Coarsen if max < coarsen_threshold
+ * && level > min_level; else Stable.  Blocking; flags is a host array [size]. */
+amrb_status amrb_pool_patch_max_flags(amrb_pool* pool, int field, double refine_threshold,
+                                      double coarsen_threshold, int min_level, int max_level,
+                                      int8_t* flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUAMR_B200_H */

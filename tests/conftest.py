@@ -1,10 +1,11 @@
+import importlib
 import os
 import sys
 
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle")):
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -29,3 +30,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def amrb():
+    """The product package (ctypes harness over lib/libgpuamr_b200.so); built on demand."""
+    mod = importlib.import_module("gpu-amr_b200")
+    if not os.path.exists(mod.LIB_PATH):
+        mod.build()
+    return mod

@@ -1,11 +1,13 @@
 // C-ABI of the device side: memory/sync wrappers, the device patch pool and all kernel launches.
 // See include/gpuamr_b200.h for the contract and the reference interfaces each group replaces.
 #include "amrb_kernels.cuh"
+#include "amrb_step_euler.cuh"
 
 #include "../../include/gpuamr_b200.h"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +47,7 @@ struct Ops
     cudaError_t (*prepare)();
     void (*halo_fill)(cudaStream_t, const FieldPtrs&, const int32_t*, const uint8_t*, int);
     void (*step)(cudaStream_t, const StepArgs&, int n_items);
+    void (*step_v1)(cudaStream_t, const StepArgs&, int n_items); // thread-per-cell variant (A/B)
     void (*compute_dt)(cudaStream_t, const StepArgs&, unsigned long long*);
     void (*plan)(cudaStream_t, const FieldPtrs&, const FieldPtrs&, const int8_t*, const int32_t*,
                  const int8_t*, int);
@@ -54,9 +57,10 @@ struct Ops
     void (*faces)(cudaStream_t, const FieldPtrs&, const int32_t*, int, double*, int);
 };
 
-template <int R, int S, int H, int EQ, int BAND>
+template <int R, int S, int H, int EQ, int BAND, int EB, int RG, int TPC, int ENT>
 struct Inst
 {
+    using EC = EulerStepCfg<R, S, H, EB, RG, TPC, ENT>;
     using G                 = Geo<R, S, H>;
     static constexpr int NV = EqTraits<EQ, R>::NV;
     static constexpr int NW = EqTraits<EQ, R>::NW;
@@ -66,6 +70,13 @@ struct Inst
 
     static cudaError_t prepare()
     {
+        if constexpr (EQ == kEqEuler)
+        {
+            cudaError_t e = cudaFuncSetAttribute(euler_step_kernel<R, S, H, EB, RG, TPC, ENT>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)EC::SMEM);
+            if (e != cudaSuccess) return e;
+        }
         return cudaFuncSetAttribute(step_kernel<R, S, H, EQ, BAND, NT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     }
@@ -74,9 +85,50 @@ struct Inst
     {
         halo_kernel<R, S, H, NV><<<n, 256, 0, st>>>(cur, nbr, meta, n);
     }
-    static void step(cudaStream_t st, const StepArgs& a, int n_items)
+    static void step_v1(cudaStream_t st, const StepArgs& a, int n_items)
     {
         step_kernel<R, S, H, EQ, BAND, NT><<<n_items * (S / BAND), NT, SMEM, st>>>(a);
+    }
+    template <int VB, int VRG, int VTPC, int VNT, int VPB, int VMINB>
+    static bool variant(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        using VC = EulerStepCfg<R, S, H, VB, VRG, VTPC, VNT>;
+        auto k   = euler_step_kernel<R, S, H, VB, VRG, VTPC, VNT, VPB, VMINB>;
+        static bool prepared = false;
+        if (!prepared)
+        {
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VC::SMEM);
+            prepared = true;
+        }
+        const int tiles = n_items * VC::NBANDS;
+        k<<<(tiles + VTPC - 1) / VTPC, VNT, VC::SMEM, st>>>(a, n_items);
+        return true;
+    }
+    static void step(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        if constexpr (EQ == kEqEuler && R == 2 && S == 64)
+        {
+            static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
+            switch (v)
+            {
+            case 1: variant<8, 2, 8, 128, 0, 3>(st, a, n_items); return;
+            case 2: variant<16, 2, 4, 256, 0, 2>(st, a, n_items); return;
+            case 3: variant<8, 4, 8, 64, 0, 3>(st, a, n_items); return;
+            case 4: variant<16, 4, 4, 256, 1, 2>(st, a, n_items); return;
+            case 5: variant<8, 4, 8, 256, 1, 3>(st, a, n_items); return;
+            case 6: variant<16, 4, 8, 128, 0, 2>(st, a, n_items); return;
+            case 7: variant<8, 4, 8, 128, 1, 3>(st, a, n_items); return;
+            default: break;
+            }
+        }
+        if constexpr (EQ == kEqEuler)
+        {
+            const int tiles = n_items * EC::NBANDS;
+            euler_step_kernel<R, S, H, EB, RG, TPC, ENT>
+                <<<(tiles + TPC - 1) / TPC, ENT, EC::SMEM, st>>>(a, n_items);
+        }
+        else
+            step_v1(st, a, n_items);
     }
     static void compute_dt(cudaStream_t st, const StepArgs& a, unsigned long long* out)
     {
@@ -104,8 +156,8 @@ struct Inst
     }
     static constexpr Ops ops()
     {
-        return Ops{ R,    S,         H,          EQ,   S / BAND, SMEM,     &prepare, &halo_fill,
-                    &step, &compute_dt, &plan, &flags, &interior, &faces };
+        return Ops{ R,     S,        H,           EQ,    S / BAND, SMEM,      &prepare, &halo_fill,
+                    &step, &step_v1, &compute_dt, &plan, &flags,   &interior, &faces };
     }
 };
 
@@ -113,19 +165,23 @@ struct Inst
 // 10x10/h2 (examples/fvm_solver_advection.e.cpp:24-53), 64x64/h1 (benchmark/
 // bench_fvm_solver_integration.b.cpp:34-63), 8^3/h1 (bench_fvm_solver_integration3D.b.cpp:31-64),
 // 16x16/h1 (KA-2D), plus the small shapes used by the parity fixtures.
+// X(rank, size, halo, band of the thread-per-cell kernel,
+//   Euler pipeline: band, rows per marching group, tiles per CTA, threads)
 #define AMRB_SHAPES(X)                                                                           \
-    X(2, 8, 1, 8)                                                                                \
-    X(2, 10, 2, 10)                                                                              \
-    X(2, 16, 1, 16)                                                                              \
-    X(2, 32, 1, 16)                                                                              \
-    X(2, 64, 1, 16)                                                                              \
-    X(3, 4, 1, 4)                                                                                \
-    X(3, 4, 2, 4)                                                                                \
-    X(3, 8, 1, 8)                                                                                \
-    X(3, 16, 1, 4)
+    X(2, 8, 1, 8, 8, 4, 8, 32)                                                                   \
+    X(2, 10, 2, 10, 10, 5, 8, 32)                                                                \
+    X(2, 16, 1, 16, 16, 4, 8, 64)                                                                \
+    X(2, 32, 1, 16, 32, 4, 4, 128)                                                               \
+    X(2, 64, 1, 16, 16, 4, 4, 128)                                                               \
+    X(3, 4, 1, 4, 4, 2, 8, 32)                                                                   \
+    X(3, 4, 2, 4, 4, 2, 8, 32)                                                                   \
+    X(3, 8, 1, 8, 8, 2, 4, 128)                                                                  \
+    X(3, 16, 1, 4, 4, 4, 4, 128)
 
 static const Ops g_ops[] = {
-#define X(R, S, H, B) Inst<R, S, H, kEqAdvection, B>::ops(), Inst<R, S, H, kEqEuler, B>::ops(),
+#define X(R, S, H, B, EB, RG, TPC, ENT)                                                          \
+    Inst<R, S, H, kEqAdvection, B, EB, RG, TPC, ENT>::ops(),                                     \
+        Inst<R, S, H, kEqEuler, B, EB, RG, TPC, ENT>::ops(),
     AMRB_SHAPES(X)
 #undef X
 };
@@ -248,7 +304,7 @@ void fill_step_args(const amrb_pool* p, StepArgs& a)
     a.level     = p->d_level;
     a.list      = nullptr;
     a.n_patches = (int)p->n_owned;
-    a.lazy_halo = (p->mode == 0) ? 1 : 0;
+    a.lazy_halo = (p->mode != 1) ? 1 : 0;
     a.gamma     = p->gamma;
     std::memcpy(a.dx, p->dx, sizeof(a.dx));
     a.sc = StepScalars{ nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, p->cfl };
@@ -527,7 +583,7 @@ uint64_t amrb_pool_launch_count(const amrb_pool* p) { return p ? p->launches : 0
 
 amrb_status amrb_pool_set_mode(amrb_pool* p, int mode)
 {
-    if (!p || (mode != 0 && mode != 1)) return fail(AMRB_ERR_ARGUMENT, "mode must be 0 or 1");
+    if (!p || mode < 0 || mode > 2) return fail(AMRB_ERR_ARGUMENT, "mode must be 0, 1 or 2");
     p->mode = mode;
     return AMRB_OK;
 }
@@ -704,7 +760,7 @@ amrb_status amrb_pool_step(amrb_pool* p, double dt)
     StepArgs a;
     fill_step_args(p, a);
     a.sc.fixed_dt = dt;
-    p->ops->step(p->stream, a, (int)p->n_owned);
+    (p->mode == 2 ? p->ops->step_v1 : p->ops->step)(p->stream, a, (int)p->n_owned);
     AMRB_TRY(check_launch(p, "step_kernel"));
     swap_buffers(p);
     p->carry_valid = false;
@@ -770,7 +826,7 @@ amrb_status amrb_pool_step_partial(amrb_pool* p, const int32_t* dev_list, size_t
     const int n_items = dev_list ? (int)count : (int)p->n_owned;
     if (n_items > 0)
     {
-        p->ops->step(p->stream, a, n_items);
+        (p->mode == 2 ? p->ops->step_v1 : p->ops->step)(p->stream, a, n_items);
         AMRB_TRY(check_launch(p, "step_kernel"));
     }
     p->step_touched = true;

@@ -169,8 +169,9 @@ amrb_status amrb_pool_finish_advance_batch(amrb_pool* pool, double* dt_sum, size
                                            double* dts, size_t dts_capacity);
 /* statistics for bench accounting: kernels launched by this pool since creation */
 uint64_t amrb_pool_launch_count(const amrb_pool* pool);
-/* select the step implementation: 0 = fused lazy-halo kernel (default),
- * 1 = unfused (materialise halos every step, then stencil) — kept for A/B measurement */
+/* select the step implementation: 0 = fused lazy-halo pipeline (default),
+ * 1 = unfused (materialise halos every step, then the same stencil kernel without gather),
+ * 2 = first-generation fused kernel (thread per cell) — 1 and 2 are kept for A/B measurement */
 amrb_status amrb_pool_set_mode(amrb_pool* pool, int mode);
 
 /* the same batch, decomposed so that a multi-GPU driver can interleave ghost-face traffic:

@@ -29,7 +29,7 @@ def _is_probe_tag(script, tag):
     return False
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["fused", "unfused"])
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["fused", "unfused", "fused_v1"])
 @pytest.mark.parametrize("name", fixtures())
 def test_device_matches_reference_dump(amrb, name, mode):
     cfg, script, g = load(name)

@@ -917,7 +917,7 @@ amrb_status amrb_pool_finish_advance_batch(amrb_pool* p, double* dt_sum, size_t*
 size_t amrb_pool_face_slab_doubles(const amrb_pool* p, int direction)
 {
     if (!p || direction < 0 || direction >= 2 * p->lay.rank) return 0;
-    size_t n = (size_t)p->lay.halo;
+    size_t n = (size_t)std::min(2 * p->lay.halo, p->lay.size[0]); // layers, see face_pack_kernel
     for (int k = 1; k < p->lay.rank; ++k) n *= (size_t)p->lay.size[0];
     return n;
 }

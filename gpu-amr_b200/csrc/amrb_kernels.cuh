@@ -782,8 +782,16 @@ interior_copy_kernel(double* __restrict__ padded, double* __restrict__ dense, in
 }
 
 // ---- inter-GPU ghost faces -----------------------------------------------------------------------------
-// entry e = {patch, direction}; slab = the H interior layers next to face `direction`, every
-// field; buffer layout [entry][field][layer][face cell]
+// entry e = {patch, direction}; slab = the T = min(2H, S) interior layers next to face `direction`,
+// every field (a finer neighbor restricts 2 fine layers per coarse ghost layer, patch_utils.hpp:
+// 334-386, so 2H layers cover all three halo operators); buffer layout [entry][field][layer][face cell]
+template <int R, int S, int H>
+struct SlabGeo
+{
+    static constexpr int T    = (2 * H < S) ? 2 * H : S;
+    static constexpr int SLAB = T * Geo<R, S, H>::FACE;
+};
+
 template <int R, int S, int H, int NV>
 __global__ void __launch_bounds__(128)
 face_pack_kernel(FieldPtrs cur, const int32_t* __restrict__ entries, int count,
@@ -794,7 +802,7 @@ face_pack_kernel(FieldPtrs cur, const int32_t* __restrict__ entries, int count,
     if (e >= count) return;
     const int     p = entries[2 * e], d = entries[2 * e + 1];
     const int     dim = d >> 1, pos = d & 1;
-    constexpr int SLAB = H * G::FACE;
+    constexpr int SLAB = SlabGeo<R, S, H>::SLAB;
     for (int it = threadIdx.x; it < NV * SLAB; it += blockDim.x)
     {
         const int f = it / SLAB, r = it % SLAB, layer = r / G::FACE;

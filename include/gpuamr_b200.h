@@ -191,9 +191,10 @@ double*     amrb_pool_dtmin_slot(amrb_pool* pool, size_t k);
 
 /* ------------------------------------------------------------------------------------------
  * 6. inter-GPU ghost faces (no reference counterpart: the reference is single-GPU).
- *    pack: gathers, for each (patch, direction) entry, the h-thick interior slab next to that
- *    face of every field into a contiguous send buffer; unpack: scatters a received buffer
- *    into the same slab of a ghost slot.  Entry = {int32 patch, int32 direction}.
+ *    pack: gathers, for each (patch, direction) entry, the min(2h, S)-thick interior slab next to
+ *    that face of every field (covers the same / coarser / finer halo operators) into a contiguous
+ *    send buffer; unpack: scatters a received buffer into the same slab of a ghost slot.
+ *    Entry = {int32 patch, int32 direction}; buffer = [entry][field][layer][face cell].
  * ---------------------------------------------------------------------------------------- */
 size_t      amrb_pool_face_slab_doubles(const amrb_pool* pool, int direction); /* per field */
 amrb_status amrb_pool_pack_faces(amrb_pool* pool, const int32_t* dev_entries, size_t count,

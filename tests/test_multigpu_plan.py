@@ -1,0 +1,139 @@
+"""Host-side logic of the Morton-range sharding (gpu-amr_b200/multigpu.py: ShardPlan): ownership,
+ghost slots, pack/unpack entry lists.  In-process cross-checks for several world sizes plus a
+world_size-2 run over torch.distributed/gloo that moves real slabs between two processes and checks
+every ghost slot against the global state."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def _tree(amrb, cfgname="r2_s8_h1_d7_euler"):
+    cfg = O.Config.from_name(cfgname)
+    t = amrb.HostTree(cfg.rank, cfg.depth)
+    for _ in range(3 if cfg.rank == 2 else 2):
+        t.reconstruct(O.flags_all(t.ids()))
+    t.reconstruct(O.flags_hash(t.ids(), 21, 300, 0, 1, 5))
+    t.reconstruct(O.flags_hash(t.ids(), 22, 250, 300, 1, 6))
+    return cfg, t
+
+
+def _slab_index(cfg, face, layers):
+    """flat padded indices of the `layers` interior layers next to `face` (dim-major like the kernel)"""
+    h, S, R = cfg.halo, cfg.size, cfg.rank
+    dim, pos = face // 2, face & 1
+    idx = np.indices((layers,) + (S,) * (R - 1)).reshape(R, -1)
+    coords, t = [None] * R, 1
+    for k in range(R):
+        if k == dim:
+            coords[k] = (h + S - 1 - idx[0]) if pos else (h + idx[0])
+        else:
+            coords[k] = h + idx[t]
+            t += 1
+    return np.ravel_multi_index(coords, (cfg.psize,) * R)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("cfgname", ["r2_s8_h1_d7_euler", "r3_s4_h1_d5_euler"])
+def test_plans_are_mutually_consistent(amrb, world, cfgname):
+    mg = importlib.import_module("gpu-amr_b200.multigpu")
+    cfg, t = _tree(amrb, cfgname)
+    levels, rel, nbr, quad = t.tables()
+    plans = [mg.ShardPlan(levels, rel, nbr, quad, r, world) for r in range(world)]
+    assert sum(p.n_owned for p in plans) == len(levels)
+    for r, p in enumerate(plans):
+        # every neighbor index is a local slot; ghosts are exactly the remote neighbors
+        used = p.nbr[p.nbr >= 0]
+        assert used.max() < p.n_total and set(used[used >= p.n_owned]) == set(range(p.n_owned, p.n_total))
+        assert len(p.interior) + len(p.boundary) == p.n_owned
+        assert (p.nbr[p.interior] < p.n_owned).all()
+        # what r sends to q is what q expects from r, in the same order
+        so = np.concatenate([[0], np.cumsum(p.send_counts)])
+        for q, pq in enumerate(plans):
+            ro = np.concatenate([[0], np.cumsum(pq.recv_counts)])
+            assert np.array_equal(p.send_global[so[q]:so[q + 1]], pq.recv_global[ro[r]:ro[r + 1]])
+        # every remote (patch, face) a halo will read is received
+        need = set()
+        for i in p.boundary:
+            for d in range(2 * cfg.rank):
+                for j in p.nbr[i, d]:
+                    if j >= p.n_owned:
+                        need.add((int(j), d ^ 1))
+        assert need == set(map(tuple, p.recv_entries.tolist()))
+
+
+def _worker(rank, world, port, cfgname, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        amrb = importlib.import_module("gpu-amr_b200")
+        mg = importlib.import_module("gpu-amr_b200.multigpu")
+        cfg, t = _tree(amrb, cfgname)
+        levels, rel, nbr, quad = t.tables()
+        p = mg.ShardPlan(levels, rel, nbr, quad, rank, world)
+        rng = np.random.default_rng(7)
+        glob = rng.random((len(levels), cfg.flat))                      # same on every rank
+        pool = np.zeros((p.n_total, cfg.flat))
+        pool[:p.n_owned] = glob[p.lo:p.hi]
+        T = min(2 * cfg.halo, cfg.size)
+        slab = [_slab_index(cfg, f, T) for f in range(2 * cfg.rank)]
+        send = np.concatenate([pool[e[0], slab[e[1]]] for e in p.send_entries]) if len(p.send_entries) else np.zeros(0)
+        n = T * cfg.size ** (cfg.rank - 1)
+        so = np.concatenate([[0], np.cumsum(p.send_counts)]) * n
+        ro = np.concatenate([[0], np.cumsum(p.recv_counts)]) * n
+        recv = np.zeros(int(ro[-1]))
+        reqs, keep = [], []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            if so[peer + 1] > so[peer]:
+                ts = torch.from_numpy(send[so[peer]:so[peer + 1]].copy())
+                keep.append(ts)
+                reqs.append(dist.isend(ts, peer))
+            if ro[peer + 1] > ro[peer]:
+                tr = torch.zeros(int(ro[peer + 1] - ro[peer]), dtype=torch.float64)
+                keep.append((tr, int(ro[peer])))
+                reqs.append(dist.irecv(tr, peer))
+        for r in reqs:
+            r.wait()
+        for k in keep:
+            if isinstance(k, tuple):
+                recv[k[1]:k[1] + len(k[0])] = k[0].numpy()
+        for e, chunk in zip(p.recv_entries, recv.reshape(-1, n)):
+            pool[e[0], slab[e[1]]] = chunk
+        ok = True
+        for e in p.recv_entries:
+            g = p.ghost_global[e[0] - p.n_owned]
+            ok &= np.array_equal(pool[e[0], slab[e[1]]], glob[g, slab[e[1]]])
+        # dt all-reduce(min) path
+        tmin = torch.tensor([1.0 + rank], dtype=torch.float64)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        ok &= float(tmin) == 1.0
+        q.put((rank, bool(ok), len(p.recv_entries)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_process_slab_exchange_gloo(amrb):
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, "r2_s8_h1_d7_euler", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res) and all(n > 0 for _, _, n in res), res

@@ -101,6 +101,11 @@ def lib():
         "amrb_pool_unpack_faces": [vp, i32p, sz, dp],
         "amrb_pool_apply_plan": [vp, sz, i8p, i32p, i8p],
         "amrb_pool_patch_max_flags": [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, i8p],
+        "amrb_patch_max_flags_device": [vp, vp, sz, sz, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp],
+        "amrb_profile_capture_start": [],
+        "amrb_profile_capture_stop": [],
+        "amrb_profile_range_push": [C.c_char_p],
+        "amrb_profile_range_pop": [],
         "amrb_tree_create": [C.c_int, C.c_int, C.POINTER(vp)],
         "amrb_tree_destroy": [vp],
         "amrb_tree_reconstruct": [vp, i8p, sz, C.POINTER(C.c_int)],
@@ -124,6 +129,8 @@ def lib():
     for name in ("amrb_pool_field", "amrb_pool_next_field"):
         getattr(L, name).argtypes = [vp, C.c_int]
         getattr(L, name).restype = vp
+    L.amrb_pool_levels.argtypes = [vp]
+    L.amrb_pool_levels.restype = vp
     L.amrb_pool_dtmin_slot.argtypes = [vp, sz]
     L.amrb_pool_dtmin_slot.restype = vp
     L.amrb_pool_launch_count.argtypes = [vp]

@@ -6,6 +6,7 @@
 #include "../../include/gpuamr_b200.h"
 
 #include <algorithm>
+#include <cuda_profiler_api.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -991,6 +992,49 @@ amrb_status amrb_pool_patch_max_flags(amrb_pool* p, int field, double refine_thr
     AMRB_TRY(check_launch(p, "patch_max_flags_kernel"));
     AMRB_CUDA(cudaMemcpyAsync(flags, p->d_flags, p->n_owned, cudaMemcpyDeviceToHost, p->stream));
     AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    return AMRB_OK;
+}
+
+amrb_status amrb_patch_max_flags_device(const double* dev_field, const int32_t* dev_levels,
+                                        size_t num_patches, size_t cells_per_patch,
+                                        double refine_threshold, double coarsen_threshold,
+                                        int min_level, int max_level, int8_t* dev_decisions,
+                                        void* stream)
+{
+    if (num_patches == 0) return AMRB_OK;
+    if (!dev_field || !dev_levels || !dev_decisions || cells_per_patch == 0)
+        return fail(AMRB_ERR_ARGUMENT, "FVM CUDA AMR inputs are smaller than the patch count");
+    patch_max_flags_rt_kernel<<<(unsigned)num_patches, 128, 0, (cudaStream_t)stream>>>(
+        dev_field, dev_levels, (int)num_patches, (int)cells_per_patch, refine_threshold,
+        coarsen_threshold, min_level, max_level, dev_decisions);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("scalar_patch_amr_kernel launch: ") + cudaGetErrorString(e));
+    return AMRB_OK;
+}
+
+const int32_t* amrb_pool_levels(const amrb_pool* p) { return p ? p->d_level : nullptr; }
+
+amrb_status amrb_profile_capture_start(void)
+{
+    AMRB_CUDA(cudaProfilerStart());
+    return AMRB_OK;
+}
+amrb_status amrb_profile_capture_stop(void)
+{
+    AMRB_CUDA(cudaProfilerStop());
+    return AMRB_OK;
+}
+// NVTX is not linked into this library; ranges are kept as a thread-local label stack so that the
+// reference's scoped_profile_range call sites stay valid.
+static thread_local std::vector<std::string> g_ranges;
+amrb_status amrb_profile_range_push(const char* label)
+{
+    g_ranges.emplace_back(label ? label : "");
+    return AMRB_OK;
+}
+amrb_status amrb_profile_range_pop(void)
+{
+    if (!g_ranges.empty()) g_ranges.pop_back();
     return AMRB_OK;
 }
 

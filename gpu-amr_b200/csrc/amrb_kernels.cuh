@@ -756,6 +756,42 @@ patch_max_flags_kernel(const double* __restrict__ field, const int32_t* __restri
     }
 }
 
+// runtime-sized variant behind the raw-pointer criterion entry point
+__global__ void __launch_bounds__(128)
+patch_max_flags_rt_kernel(const double* __restrict__ field, const int32_t* __restrict__ level,
+                          int n_patches, int flat, double refine_thr, double coarsen_thr,
+                          int min_level, int max_level, int8_t* __restrict__ flags)
+{
+    __shared__ double red[4];
+    const int p = blockIdx.x;
+    if (p >= n_patches) return;
+    double m = -DBL_MAX;
+    for (int i = threadIdx.x; i < flat; i += 128)
+    {
+        const double v = field[(size_t)p * flat + i];
+        m              = v > m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double t = __shfl_xor_sync(0xffffffffu, m, o);
+        m              = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int i = 1; i < 4; ++i) m = red[i] > m ? red[i] : m;
+        const int lv = level[p];
+        int8_t    fl = 0;
+        if (lv < max_level && m > refine_thr)
+            fl = 1;
+        else if (lv > min_level && m < coarsen_thr)
+            fl = 2;
+        flags[p] = fl;
+    }
+}
+
 // ---- interior <-> padded (host staging helpers) -------------------------------------------------------
 template <int R, int S, int H>
 __global__ void __launch_bounds__(256)

@@ -244,6 +244,28 @@ amrb_status amrb_pool_patch_max_flags(amrb_pool* pool, int field, double refine_
                                       double coarsen_threshold, int min_level, int max_level,
                                       int8_t* flags);
 
+/* raw-pointer form of the same criterion — replaces
+ * amr::cuda::compute_scalar_patch_amr_decisions_from_device
+ * (include/cuda/fvm_refinement_criterion.hpp:20-27): all pointers are device pointers,
+ * decisions[i] in AMRB_{STABLE,REFINE,COARSEN}; asynchronous on `stream` (NULL = default). */
+amrb_status amrb_patch_max_flags_device(const double* dev_field, const int32_t* dev_levels,
+                                        size_t num_patches, size_t cells_per_patch,
+                                        double refine_threshold, double coarsen_threshold,
+                                        int min_level, int max_level, int8_t* dev_decisions,
+                                        void* stream);
+/* device pointer of the per-patch level array uploaded by amrb_pool_set_topology
+ * (ndtree::get_device_patch_level_buffer, ndtree.hpp:659-678) */
+const int32_t* amrb_pool_levels(const amrb_pool* pool);
+
+/* ------------------------------------------------------------------------------------------
+ * 8. profiling hooks — replaces amr::cuda::profile_capture_{start,stop}, profile_range_{push,pop}
+ *    (include/cuda/profiler.hpp, src/cuda/device_buffer.cu:229-237)
+ * ---------------------------------------------------------------------------------------- */
+amrb_status amrb_profile_capture_start(void);
+amrb_status amrb_profile_capture_stop(void);
+amrb_status amrb_profile_range_push(const char* label);
+amrb_status amrb_profile_range_pop(void);
+
 #ifdef __cplusplus
 }
 #endif

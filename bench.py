@@ -142,8 +142,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(cells, extra=None):
-    c = {"workload": "C2: bench_fvm_solver_integration 2D static multi-level tree, Euler fp64, "
+def workload_config(cells, extra=None, name=None):
+    c = {"workload": ("development workload " + name) if name else
+                     "C2: bench_fvm_solver_integration 2D static multi-level tree, Euler fp64, "
                      "64x64 patches halo 1, levels 5-7, acoustic pulse",
          "cells": int(cells), "l2_policy": "inputs larger than L2 (state 2 x 0.4 GB vs 126 MB)"}
     if extra:
@@ -205,8 +206,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     peaks, peak_src = measured_peaks()
 
-    cfg = wl.c2_config()
-    host = wl.build_static_tree(cfg, wl.C2["base_level"], wl.C2["ball_radii"])
+    if args.workload == "c2":
+        cfg = wl.c2_config()
+        host = wl.build_static_tree(cfg, wl.C2["base_level"], wl.C2["ball_radii"])
+    else:
+        # development workloads (not the driver's bench line): name = r<rank>_s<size>_h<halo>_<eq>_L<base>[m]
+        # e.g. r3_s8_h1_euler_L5m = 3D Euler 8^3 patches, uniform level 5 + two refinement rings
+        t = args.workload.split("_")
+        rank, size, halo = int(t[0][1:]), int(t[1][1:]), int(t[2][1:])
+        eq = amrb.EQ_EULER if t[3] == "euler" else amrb.EQ_ADVECTION
+        base, multi = int(t[4][1:].rstrip("m")), t[4].endswith("m")
+        cfg = wl.Config(rank, size, halo, 7 if rank == 2 else 7, eq)
+        host = wl.build_static_tree(cfg, base, (0.25, 0.125) if multi else ())
     ids = host.ids()
     P = len(ids)
     cells = P * cfg.data
@@ -292,7 +303,7 @@ def run_ours(args):
     achieved = cells * b_alg / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(),
-                "kernel": "step_kernel<2,64,1,euler>", "kernel_ms": kern_ms, "kernel_ms_median": per[len(per) // 2],
+                "kernel": "fused step kernel (euler2d_march_kernel<64,1,band> for C2)", "kernel_ms": kern_ms, "kernel_ms_median": per[len(per) // 2],
                 "algorithmic_bytes_per_cell": b_alg, "peak_source": peak_src}
 
     # ---- (3) end to end through the C ABI with HOST buffers: sync_current_to_device (pinned H2D of
@@ -315,12 +326,13 @@ def run_ours(args):
            "what": "pinned-host H2D of the padded state + halo fill + %d steps + D2H of the state, "
                    "one job (the reference benchmark copies state once per run, b.cpp:194-197)" % K}
 
-    cpu = cpu_baseline_leg(wl) if not args.no_cpu_baseline else None
+    cpu = cpu_baseline_leg(wl) if (not args.no_cpu_baseline and args.workload == "c2") else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(cells, {"patches": P, "executed_steps": int(executed), "sum_dt": dt_sum}),
+        "config": workload_config(cells, {"patches": P, "executed_steps": int(executed), "sum_dt": dt_sum},
+                                  None if args.workload == "c2" else args.workload),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clk, "wall_s_timed": t_wall1 - t_wall0, "repetitions_ms": reps_ms,
     }
@@ -346,6 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", help="c2 (bench line) or a development workload name")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 20 if args.steps is None else args.steps

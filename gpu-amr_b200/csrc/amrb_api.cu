@@ -2,10 +2,12 @@
 // See include/gpuamr_b200.h for the contract and the reference interfaces each group replaces.
 #include "amrb_kernels.cuh"
 #include "amrb_step_euler.cuh"
+#include "amrb_march_euler.cuh"
 
 #include "../../include/gpuamr_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cuda_profiler_api.h>
 #include <cstdio>
 #include <cstdlib>
@@ -90,36 +92,71 @@ struct Inst
     {
         step_kernel<R, S, H, EQ, BAND, NT><<<n_items * (S / BAND), NT, SMEM, st>>>(a);
     }
-    template <int VB, int VRG, int VTPC, int VNT, int VPB, int VMINB>
-    static bool variant(cudaStream_t st, const StepArgs& a, int n_items)
+    // warp-autonomous marching kernel (amrb_march_euler.cuh): persistent grid, MINB CTAs per SM
+    static int sm_count()
     {
-        using VC = EulerStepCfg<R, S, H, VB, VRG, VTPC, VNT>;
-        auto k   = euler_step_kernel<R, S, H, VB, VRG, VTPC, VNT, VPB, VMINB>;
+        static int sms = 0;
+        if (sms == 0)
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        return sms;
+    }
+    template <int BANDM, int CR, int NS, int WPC, int MINB>
+    static void march(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        using MC = March2Cfg<S, H, BANDM, CR, NS, WPC>;
+        auto k   = euler2d_march_kernel<S, H, BANDM, CR, NS, WPC, MINB>;
         static bool prepared = false;
         if (!prepared)
         {
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VC::SMEM);
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MC::SMEM);
             prepared = true;
         }
-        const int tiles = n_items * VC::NBANDS;
-        k<<<(tiles + VTPC - 1) / VTPC, VNT, VC::SMEM, st>>>(a, n_items);
-        return true;
+        const int tasks = n_items * MC::NB;
+        const int grid  = std::max(1, std::min(sm_count() * MINB, (tasks + WPC - 1) / WPC));
+        k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
+    }
+    // Task height of the marching kernel: taller bands stream fewer halo rows (2 per band) and
+    // store longer contiguous runs; shorter bands balance small meshes over the 8 warps x SMs.
+    // score = wave efficiency / (1 + 2 / band)
+    static int pick_band(int n_items)
+    {
+        const double warps = 8.0 * sm_count();
+        int          best = 16;
+        double       best_score = 0.0;
+        for (int band : { 64, 32, 16 })
+        {
+            const double rounds = n_items * (double)(S / band) / warps;
+            const double eff    = rounds / std::ceil(rounds);
+            const double score  = eff / (1.0 + 2.0 / band);
+            if (score > best_score * 1.0001)
+            {
+                best_score = score;
+                best       = band;
+            }
+        }
+        return best;
     }
     static void step(cudaStream_t st, const StepArgs& a, int n_items)
     {
-        if constexpr (EQ == kEqEuler && R == 2 && S == 64)
+        if constexpr (EQ == kEqEuler && R == 2 && S == 64 && H == 1)
         {
+            // AMRB_VARIANT: 0 = marching kernel, band chosen per launch (default); 1/2/3 = marching
+            // kernel with 16/32/64-row bands; 10 = block-cooperative pipeline (second generation)
             static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
-            switch (v)
+            const int band = (v == 1) ? 16 : (v == 2) ? 32 : (v == 3) ? 64 : pick_band(n_items);
+            if (v != 10)
             {
-            case 1: variant<8, 2, 8, 128, 0, 3>(st, a, n_items); return;
-            case 2: variant<16, 2, 4, 256, 0, 2>(st, a, n_items); return;
-            case 3: variant<8, 4, 8, 64, 0, 3>(st, a, n_items); return;
-            case 4: variant<16, 4, 4, 256, 1, 2>(st, a, n_items); return;
-            case 5: variant<8, 4, 8, 256, 1, 3>(st, a, n_items); return;
-            case 6: variant<16, 4, 8, 128, 0, 2>(st, a, n_items); return;
-            case 7: variant<8, 4, 8, 128, 1, 3>(st, a, n_items); return;
-            default: break;
+                if (band == 64)
+                    march<64, 2, 3, 4, 2>(st, a, n_items);
+                else if (band == 32)
+                    march<32, 2, 3, 4, 2>(st, a, n_items);
+                else
+                    march<16, 2, 3, 4, 2>(st, a, n_items);
+                return;
             }
         }
         if constexpr (EQ == kEqEuler)

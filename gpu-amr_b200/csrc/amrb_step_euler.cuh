@@ -382,6 +382,17 @@ euler_step_kernel(const __grid_constant__ StepArgs a, int n_items)
                     n[f]            = Cc.u[f] + up[f];
                     a.nxt.p[f][gl] = n[f];
                 }
+                {
+                    const int xi = ci % S;
+                    if (xi == 0 || xi == S - 1)
+                    {
+                        const int dir = (xi == 0) ? -1 : 1;
+#pragma unroll
+                        for (int f = 0; f < NV; ++f)
+#pragma unroll
+                            for (int h = 1; h <= H; ++h) a.nxt.p[f][gl + dir * h] = n[f];
+                    }
+                }
                 const double irho = fast_rcp(n[0]);
                 double       K    = 0.0;
 #pragma unroll
@@ -402,6 +413,7 @@ euler_step_kernel(const __grid_constant__ StepArgs a, int n_items)
             const int grp = it / C::NQ;
             const int q   = it % C::NQ;
             int       cross; // offset of cell A inside a slowest-dim row
+            const int xq = (R == 2) ? q : q % (S / 2); // index of the cell pair along x
             if constexpr (R == 2)
                 cross = H + 2 * q;
             else
@@ -464,6 +476,22 @@ euler_step_kernel(const __grid_constant__ StepArgs a, int n_items)
                     GmB[f] = GuB[f];
                     a.nxt.p[f][go]     = nA[f];
                     a.nxt.p[f][go + 1] = nB[f];
+                }
+                // whole padded x-rows are stored (ghost columns = copy of the adjacent cell): full
+                // 32-byte sectors, see step_kernel
+                if (xq == 0)
+                {
+#pragma unroll
+                    for (int f = 0; f < NV; ++f)
+#pragma unroll
+                        for (int h = 1; h <= H; ++h) a.nxt.p[f][go - h] = nA[f];
+                }
+                if (xq == S / 2 - 1)
+                {
+#pragma unroll
+                    for (int f = 0; f < NV; ++f)
+#pragma unroll
+                        for (int h = 1; h <= H; ++h) a.nxt.p[f][go + 1 + h] = nB[f];
                 }
                 // wave speed of the new state (EulerPhysics.hpp:137-161)
 #pragma unroll

@@ -3,6 +3,7 @@
 #include "amrb_kernels.cuh"
 #include "amrb_step_euler.cuh"
 #include "amrb_march_euler.cuh"
+#include "amrb_march_euler3d.cuh"
 
 #include "../../include/gpuamr_b200.h"
 
@@ -140,8 +141,40 @@ struct Inst
         }
         return best;
     }
+    // 3D warp-autonomous plane-marching kernel (amrb_march_euler3d.cuh)
+    template <int CR, int NS, int WPC, int MINB>
+    static void march3(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        using MC = March3Cfg<S, H, CR, NS, WPC>;
+        auto k   = euler3d_march_kernel<S, H, CR, NS, WPC, MINB>;
+        static bool prepared = false;
+        if (!prepared)
+        {
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MC::SMEM);
+            prepared = true;
+        }
+        const int tasks = n_items * MC::NB;
+        const int grid  = std::max(1, std::min(sm_count() * MINB, (tasks + WPC - 1) / WPC));
+        k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
+    }
     static void step(cudaStream_t st, const StepArgs& a, int n_items)
     {
+        if constexpr (EQ == kEqEuler && R == 3 && H == 1 && S % 8 == 0)
+        {
+            // AMRB_VARIANT: 0 = plane-marching kernel (default); 11/12 = other ring shapes;
+            // 10 = block-cooperative pipeline (second generation)
+            static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
+            if (v != 10)
+            {
+                if (v == 11)
+                    march3<1, 4, 4, 2>(st, a, n_items);
+                else if (v == 12)
+                    march3<1, 3, 4, 3>(st, a, n_items);
+                else
+                    march3<(S == 8 ? 2 : 1), (S == 8 ? 2 : 4), 4, 2>(st, a, n_items);
+                return;
+            }
+        }
         if constexpr (EQ == kEqEuler && R == 2 && S == 64 && H == 1)
         {
             // AMRB_VARIANT: 0 = marching kernel, band chosen per launch (default); 1/2/3 = marching

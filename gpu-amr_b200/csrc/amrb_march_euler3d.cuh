@@ -1,0 +1,737 @@
+// Fused Euler step, third generation (3D): warp-autonomous plane marching.
+//
+// The 3D form of euler2d_march_kernel (amrb_march_euler.cuh):
+//   * task = one 8 x 8 (x, y) column block of one patch, all S planes along z (the slowest layout
+//     dim); an 8^3 patch is one task, a 16^3 patch four.  A warp walks its tasks back to back and
+//     never meets a block barrier.
+//   * the planes of a task stream through a warp-private shared-memory ring of NS stages filled by
+//     TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): for 8^3 patches one copy per
+//     field moves CR whole padded planes (contiguous in the pool), for wider patches one copy per
+//     field-plane moves the block's 8 padded rows.  Only the S interior planes are streamed; the
+//     ghost planes below / above are never read from the pool.
+//   * lane = (y row 0..7) x (x pair 0..3): a lane owns two x-adjacent cells of the plane and marches
+//     them along z.  The cell record (U, p, a, 1/rho) is derived once, in registers; the z-face
+//     flux is carried in registers (folded into the running update); x-faces as in 2D (left
+//     lane's p / a / 1/rho and the right lane's left flux by warp shuffle); the lower y-face uses
+//     the record of lane-4 (U from the staged plane, p / a / 1/rho by shuffle), the upper y-face
+//     flux is lane+4's lower flux by shuffle: every interior face flux is computed exactly once.
+//   * ghost cells are never written: the 32 lateral boundary faces of a plane (8 per side) are one
+//     per lane -- lane = side x position gathers the ghost cell straight from the neighbor patch
+//     interior through the halo tables (same / coarser injection / finer restriction, reference
+//     summation order) or, for a block boundary inside the patch, from the patch itself, computes
+//     that face's flux and parks it in a double-buffered 1.5 KB array; the loads for plane z+1
+//     are issued before plane z is computed.  Ghost planes across the z faces are gathered into
+//     the registers of the lanes that march those columns.
+//   * stores cover whole padded planes (ghost rows / columns get copies of the adjacent cell):
+//     the interior planes of a field-patch are then one contiguous run of fully written 32-byte
+//     sectors (see the 2D kernel for the measured reason).
+//
+// Arithmetic follows include/solver/EulerPhysics.hpp:74-129 and amr_solver.hpp:265-353 of the
+// reference; 0.5 of the Rusanov flux is folded into dt/dx (exact); the update is accumulated as
+// ((U + hx dFx) + hy dFy) - hz Fz_low + hz Fz_up with fused multiply-adds (rounding-level
+// difference from the reference's association; parity bound 1e-12 field-max-normalised).
+#pragma once
+#include "amrb_march_euler.cuh"
+
+namespace amrb
+{
+
+// per-thread 8-byte asynchronous copy global -> shared (SASS LDGSTS): no register staging, the
+// load is in flight as soon as it is issued
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct Cell3
+{
+    double u[5];
+    double p, a, ir;
+};
+
+__device__ __forceinline__ void prims3(Cell3& c, double g, double gm1)
+{
+    c.ir     = rcp_nr2(c.u[0]);
+    double K = c.u[1] * c.u[1];
+    K        = fma(c.u[2], c.u[2], K);
+    K        = fma(c.u[3], c.u[3], K);
+    K *= 0.5 * c.ir;
+    c.p = gm1 * (c.u[4] - K);
+    c.a = sqrt_nr2(g * c.p * c.ir);
+}
+
+// G = F(L) + F(R) - smax (U_R - U_L) across a face normal to solver direction DS (0 x, 1 y, 2 z)
+template <int DS>
+__device__ __forceinline__ void flux3(const Cell3& L, const Cell3& R, double (&G)[5])
+{
+    const double uL = L.u[1 + DS] * L.ir, uR = R.u[1 + DS] * R.ir;
+    const double sm = pos_max(fabs(uL) + L.a, fabs(uR) + R.a);
+    G[0]            = (L.u[1 + DS] + R.u[1 + DS]) - sm * (R.u[0] - L.u[0]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        double fl = L.u[1 + k] * uL, fr = R.u[1 + k] * uR;
+        if (k == DS)
+        {
+            fl += L.p;
+            fr += R.p;
+        }
+        G[1 + k] = (fl + fr) - sm * (R.u[1 + k] - L.u[1 + k]);
+    }
+    const double eL = uL * (L.u[4] + L.p), eR = uR * (R.u[4] + R.p);
+    G[4]            = (eL + eR) - sm * (R.u[4] - L.u[4]);
+}
+
+// same, face normal chosen at run time between x (ds = 0) and y (ds = 1): the lateral boundary
+// faces of a plane are spread over the lanes of one warp
+__device__ __forceinline__ void flux3_xy(const Cell3& L, const Cell3& R, int ds, double (&G)[5])
+{
+    const double mL = ds ? L.u[2] : L.u[1], mR = ds ? R.u[2] : R.u[1];
+    const double uL = mL * L.ir, uR = mR * R.ir;
+    const double sm = pos_max(fabs(uL) + L.a, fabs(uR) + R.a);
+    const double pLx = ds ? 0.0 : L.p, pRx = ds ? 0.0 : R.p;
+    const double pLy = ds ? L.p : 0.0, pRy = ds ? R.p : 0.0;
+    G[0]            = (mL + mR) - sm * (R.u[0] - L.u[0]);
+    G[1]            = (fma(L.u[1], uL, pLx) + fma(R.u[1], uR, pRx)) - sm * (R.u[1] - L.u[1]);
+    G[2]            = (fma(L.u[2], uL, pLy) + fma(R.u[2], uR, pRy)) - sm * (R.u[2] - L.u[2]);
+    G[3]            = (L.u[3] * uL + R.u[3] * uR) - sm * (R.u[3] - L.u[3]);
+    const double eL = uL * (L.u[4] + L.p), eR = uR * (R.u[4] + R.p);
+    G[4]            = (eL + eR) - sm * (R.u[4] - L.u[4]);
+}
+
+// Restriction of one ghost cell for all 5 fields: mean of the 2^3 fine cells at offset `o`, summed
+// last-dim-fastest like hypercube_offset (patch_utils.hpp:203-234, intergrid_operator.hpp:92-106).
+// Kept out of line: coarse/fine faces are a small minority of all faces and the marching loop has
+// to stay inside the instruction cache.
+__device__ __noinline__ void fine_mean5(const FieldPtrs& cur, size_t o, int P, int PP, double* out)
+{
+#pragma unroll 1
+    for (int f = 0; f < 5; ++f)
+    {
+        const double* __restrict__ s = cur.p[f] + o;
+        double sum = 0.0;
+        sum += __ldg(s);
+        sum += __ldg(s + 1);
+        sum += __ldg(s + P);
+        sum += __ldg(s + P + 1);
+        sum += __ldg(s + PP);
+        sum += __ldg(s + PP + 1);
+        sum += __ldg(s + PP + P);
+        sum += __ldg(s + PP + P + 1);
+        out[f] = sum / 8.0;
+    }
+}
+
+// where a boundary ghost cell of plane z is gathered from (resolved once per task)
+struct GhostSrc3
+{
+    int q0, q1; // source patch for z in the lower / upper half of the patch (finer), else equal
+    int off;    // (y, x) offset inside the source plane
+    int zbase;  // single source: plane zbase + (z >> zshift); finer: plane H + 2 (z mod S/2)
+    int zshift;
+    int finer;
+};
+
+template <int S, int H, int CR, int NS, int WPC>
+struct March3Cfg
+{
+    using G                    = Geo<3, S, H>;
+    static constexpr int NV    = 5;
+    static constexpr int P     = G::P;
+    static constexpr int PP    = P * P;
+    static constexpr int NBX   = S / 8, NBY = S / 8;
+    static constexpr int NB    = NBX * NBY;            // tasks per patch
+    static constexpr bool WHOLE = (NB == 1);           // stream whole padded planes
+    static constexpr int PLD   = WHOLE ? PP : 8 * P;   // doubles per staged field-plane
+    static constexpr int ROW0  = WHOLE ? H : 0;        // staged row of the block's first row
+    static constexpr int NCH   = S / CR;               // chunks per task
+    static constexpr int STAGE = NV * CR * PLD;
+    static constexpr int RING  = NS * STAGE;
+    static constexpr int BFW   = 6;                    // doubles per parked boundary flux (5 + pad)
+    static constexpr int BF    = 2 * 32 * BFW;         // double-buffered, 32 faces per plane
+    static constexpr int ST    = 2 * 10 * 32;          // boundary-face inputs in flight: [2][10][32]
+    static constexpr int WARP_DOUBLES = RING + BF + ST;
+    static constexpr size_t SMEM      = (size_t)WPC * WARP_DOUBLES * sizeof(double);
+    static_assert(S % 8 == 0 && S % 2 == 0, "8 x 8 column blocks");
+    static_assert(H == 1, "odd ghost width: (ghost|first) and (second|right) pairs are 16-byte aligned");
+    static_assert(S % CR == 0, "chunk shape");
+    static_assert((PLD * 8) % 16 == 0 && (WARP_DOUBLES * 8) % 16 == 0, "bulk copy alignment");
+};
+
+template <int S, int H, int CR, int NS, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
+{
+    using C           = March3Cfg<S, H, CR, NS, WPC>;
+    using G           = Geo<3, S, H>;
+    constexpr int NV  = 5;
+    constexpr int P   = C::P;
+    constexpr int PP  = C::PP;
+    constexpr int PLD = C::PLD;
+    constexpr int FS  = CR * PLD; // field stride inside a stage
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[WPC * NS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int xq = lane & 3, yy = lane >> 2;   // marching role: x pair, y row of the block
+    const int side = lane >> 3, bt = lane & 7; // boundary-face role: side (x-,x+,y-,y+), position
+    double*   ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::WARP_DOUBLES;
+    double*   sBF  = ring + C::RING;
+    double*   sST  = sBF + C::BF + lane; // this lane's column of the staging buffer
+    uint64_t* bar  = bars + warp * NS;
+
+    // ---- this warp's tasks: the CTA owns a contiguous task range, its warps interleave
+    const int n_tasks = n_items * C::NB;
+    const int tb      = (int)((long long)n_tasks * blockIdx.x / gridDim.x);
+    const int te      = (int)((long long)n_tasks * (blockIdx.x + 1) / gridDim.x);
+    const int nt      = (te - tb > warp) ? (te - tb - warp + WPC - 1) / WPC : 0;
+
+    auto task_of = [&](int k, int& p, int& bx, int& by) {
+        const int tau  = tb + warp + k * WPC;
+        const int item = tau / C::NB;
+        const int blk  = tau % C::NB;
+        bx             = blk % C::NBX;
+        by             = blk / C::NBX;
+        p              = a.list ? a.list[item] : item;
+    };
+
+    if (lane == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
+    }
+    __syncwarp();
+
+    // ---- producer side of the ring (lane 0 issues; all lanes track the counters)
+    int  ik = 0, ic = 0, ist = 0; // next chunk to issue: task, chunk in task, stage
+    auto issue_next = [&]() {
+        if (ik >= nt) return;
+        int p, bx, by;
+        task_of(ik, p, bx, by);
+        if (lane == 0)
+        {
+            double* dst = ring + ist * C::STAGE;
+            mbar_expect_tx(&bar[ist], C::STAGE * 8);
+            if constexpr (C::WHOLE)
+            {
+                const size_t go = (size_t)p * G::FLAT + (size_t)(H + ic * CR) * PP;
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                    bulk_g2s(dst + f * FS, a.cur.p[f] + go, FS * 8, &bar[ist]);
+            }
+            else
+            {
+                const size_t go =
+                    (size_t)p * G::FLAT + (size_t)(H + ic * CR) * PP + (size_t)(H + 8 * by) * P;
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+#pragma unroll
+                    for (int j = 0; j < CR; ++j)
+                        bulk_g2s(dst + f * FS + j * PLD, a.cur.p[f] + go + (size_t)j * PP, PLD * 8,
+                                 &bar[ist]);
+            }
+        }
+        if (++ic == C::NCH)
+        {
+            ic = 0;
+            ++ik;
+        }
+        if (++ist == NS) ist = 0;
+    };
+#pragma unroll
+    for (int s = 0; s < NS; ++s) issue_next();
+
+    // ---- step scalars
+    double       rem_after;
+    const double dt = resolve_step_dt(a.sc, rem_after);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.sc.dtmin_in != nullptr)
+    {
+        *a.sc.dt_taken      = dt;
+        *a.sc.remaining_out = rem_after;
+    }
+    const double g = a.gamma, gm1 = a.gamma - 1.0;
+    double       cand = DBL_MAX; // min dx/speed over finished levels
+    double       sxm = 0.0, sym = 0.0, szm = 0.0;
+    int          lvl_prev = -1;
+
+    int cst = 0, cph = 0; // consumer: stage and phase parity of the next chunk to wait for
+
+    for (int k = 0; k < nt; ++k)
+    {
+        int p, bx, by;
+        task_of(k, p, bx, by);
+        const int lvl = a.level[p];
+        if (lvl != lvl_prev && lvl_prev >= 0)
+        {
+            if (sxm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][0] / sxm);
+            if (sym > 1e-12) cand = fmin(cand, a.dx[lvl_prev][1] / sym);
+            if (szm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][2] / szm);
+            sxm = sym = szm = 0.0;
+        }
+        lvl_prev         = lvl;
+        const double hx  = -0.5 * (dt / a.dx[lvl][0]); // -0.5 dt/dx, x = fastest layout dim
+        const double hy  = -0.5 * (dt / a.dx[lvl][1]);
+        const double hz  = -0.5 * (dt / a.dx[lvl][2]);
+        const double nhz = -hz;
+        const size_t pb  = (size_t)p * G::FLAT;
+        const int    x0 = 8 * bx, y0 = 8 * by;
+
+        // ---- boundary-face role of this lane for the task: where the ghost cell of plane z
+        // comes from, resolved ONCE per task into a compact descriptor (the halo tables are not
+        // touched inside the plane loop)
+        const int  bd       = (side < 2) ? 4 + side : side; // tree direction of the side
+        const bool internal = (side == 0)   ? (bx > 0)
+                              : (side == 1) ? (bx < C::NBX - 1)
+                              : (side == 2) ? (by > 0)
+                                            : (by < C::NBY - 1);
+        int g_y, g_x, i_y, i_x; // padded (y, x) of the ghost / interior cell of the face
+        if (side < 2)
+        {
+            g_y = i_y = H + y0 + bt;
+            g_x       = side ? H + x0 + 8 : H + x0 - 1;
+            i_x       = side ? H + x0 + 7 : H + x0;
+        }
+        else
+        {
+            g_x = i_x = H + x0 + bt;
+            g_y       = (side == 3) ? H + y0 + 8 : H + y0 - 1;
+            i_y       = (side == 3) ? H + y0 + 7 : H + y0;
+        }
+        const int ioff = i_y * P + i_x;
+        GhostSrc3 gs;
+        {
+            const int bm  = a.meta[(size_t)p * G::NDIR + bd];
+            const int rel = (!internal && a.lazy_halo) ? (bm & 3) : 0;
+            const int32_t* bnb = a.nbr + ((size_t)p * G::NDIR + bd) * G::KF;
+            int f_y = g_y, f_x = g_x; // mirrored into the neighbor's frame (patch_utils.hpp:322-327)
+            if (side < 2)
+                f_x += (side & 1) ? -S : S;
+            else
+                f_y += (side & 1) ? -S : S;
+            gs.finer  = 0;
+            gs.zshift = 0;
+            gs.zbase  = H;
+            if (rel == 0)
+            {
+                // own patch: block side inside the patch, relation 'none', or materialised halos
+                gs.q0 = gs.q1 = p;
+                gs.off        = g_y * P + g_x;
+            }
+            else if (rel == 1)
+            {
+                gs.q0 = gs.q1 = bnb[0]; // same_t (patch_utils.hpp:315-332)
+                gs.off        = f_y * P + f_x;
+            }
+            else if (rel == 3)
+            {
+                // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
+                const int qz = (bm >> 2) & 1, qy = (bm >> 3) & 1, qx = (bm >> 4) & 1;
+                gs.q0 = gs.q1 = bnb[0];
+                gs.off = (H + qy * (S / 2) + (f_y - H) / 2) * P + (H + qx * (S / 2) + (f_x - H) / 2);
+                gs.zbase  = H + qz * (S / 2);
+                gs.zshift = 1;
+            }
+            else
+            {
+                // finer_t: mean of 8 fine cells (patch_utils.hpp:334-386); finer-neighbor index =
+                // z half (bit 0) + 2 x half along the other tangential dim (neighbor.hpp:316-337)
+                const int t = ((side < 2) ? (g_y - H) : (g_x - H)) / (S / 2);
+                gs.q0       = bnb[2 * t];
+                gs.q1       = bnb[2 * t + 1];
+                gs.off      = ((((f_y - H) * 2) % S) + H) * P + (((f_x - H) * 2) % S) + H;
+                gs.finer    = 1;
+            }
+        }
+        // issue the loads of this lane's boundary face of plane z (ghost + interior cell, all
+        // fields) into staging buffer z & 1; they land asynchronously (cp.async group)
+        auto bnd_issue = [&](int z) {
+            double* st = sST + (z & 1) * 320;
+            if (gs.finer)
+            {
+                const size_t o = (size_t)(z < S / 2 ? gs.q0 : gs.q1) * G::FLAT +
+                                 (size_t)(H + 2 * (z % (S / 2))) * PP + gs.off;
+                double t[NV];
+                fine_mean5(a.cur, o, P, PP, t);
+#pragma unroll
+                for (int f = 0; f < NV; ++f) st[f * 32] = t[f];
+            }
+            else
+            {
+                const size_t o =
+                    (size_t)gs.q0 * G::FLAT + (size_t)(gs.zbase + (z >> gs.zshift)) * PP + gs.off;
+#pragma unroll
+                for (int f = 0; f < NV; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
+            }
+            const size_t zo = pb + (size_t)(H + z) * PP + ioff;
+#pragma unroll
+            for (int f = 0; f < NV; ++f) cp_async8(st + (NV + f) * 32, a.cur.p[f] + zo);
+        };
+        // flux of this lane's boundary face of plane z from the staged cells -> sBF[z & 1].
+        // G = F(ghost) + F(interior) -/+ smax (U_interior - U_ghost): the Rusanov flux is symmetric
+        // in the two cells except for the sign of the dissipation term (low sides: ghost is the
+        // left cell), so one branch-free evaluation serves all four sides.
+        const double bsgn = (side & 1) ? -1.0 : 1.0;
+        auto bnd_flux = [&](int z) {
+            const double* st = sST + (z & 1) * 320;
+            Cell3         gc, ic_;
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                gc.u[f]  = st[f * 32];
+                ic_.u[f] = st[(NV + f) * 32];
+            }
+            prims3(gc, g, gm1);
+            prims3(ic_, g, gm1);
+            const int    ds = side >> 1;
+            const double mG = ds ? gc.u[2] : gc.u[1], mI = ds ? ic_.u[2] : ic_.u[1];
+            const double uG = mG * gc.ir, uI = mI * ic_.ir;
+            const double sm = bsgn * pos_max(fabs(uG) + gc.a, fabs(uI) + ic_.a);
+            const double pGx = ds ? 0.0 : gc.p, pIx = ds ? 0.0 : ic_.p;
+            const double pGy = ds ? gc.p : 0.0, pIy = ds ? ic_.p : 0.0;
+            double       F[NV];
+            F[0] = (mG + mI) + sm * (gc.u[0] - ic_.u[0]);
+            F[1] = (fma(gc.u[1], uG, pGx) + fma(ic_.u[1], uI, pIx)) + sm * (gc.u[1] - ic_.u[1]);
+            F[2] = (fma(gc.u[2], uG, pGy) + fma(ic_.u[2], uI, pIy)) + sm * (gc.u[2] - ic_.u[2]);
+            F[3] = (gc.u[3] * uG + ic_.u[3] * uI) + sm * (gc.u[3] - ic_.u[3]);
+            F[4] = (uG * (gc.u[4] + gc.p) + uI * (ic_.u[4] + ic_.p)) + sm * (gc.u[4] - ic_.u[4]);
+            double2* o = reinterpret_cast<double2*>(sBF + ((z & 1) * 32 + lane) * C::BFW);
+            o[0]       = make_double2(F[0], F[1]);
+            o[1]       = make_double2(F[2], F[3]);
+            o[2]       = make_double2(F[4], 0.0);
+        };
+        // ghost cells of this lane's column pair across the z faces (d = 0 below, 1 above)
+        auto zghost = [&](int d, double (&vA)[NV], double (&vB)[NV]) {
+            const int      m   = a.meta[(size_t)p * G::NDIR + d];
+            const int32_t* nb  = a.nbr + ((size_t)p * G::NDIR + d) * G::KF;
+            const int      rel = a.lazy_halo ? (m & 3) : 0;
+            const int      y = H + y0 + yy, x = H + x0 + 2 * xq;
+            const int      zi = d ? H + S : H - 1, zf = d ? H : H + S - 1; // ghost plane, mirrored
+            int            q = p, dB = 1, fin = 0;
+            int            off = zi * PP + y * P + x;
+            if (rel == 1)
+            {
+                q   = nb[0];
+                off = zf * PP + y * P + x;
+            }
+            else if (rel == 3)
+            {
+                const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
+                q   = nb[0];
+                off = (H + qz * (S / 2) + (zf - H) / 2) * PP + (H + qy * (S / 2) + (y - H) / 2) * P +
+                      (H + qx * (S / 2) + (x - H) / 2);
+                dB = 0;
+            }
+            else if (rel == 2)
+            {
+                q   = nb[(y - H) / (S / 2) + 2 * ((x - H) / (S / 2))];
+                off = ((((zf - H) * 2) % S) + H) * PP + ((((y - H) * 2) % S) + H) * P +
+                      (((x - H) * 2) % S) + H;
+                dB  = 2;
+                fin = 1;
+            }
+            const size_t o = (size_t)q * G::FLAT + off;
+            if (fin)
+            {
+                double tA[NV], tB[NV];
+                fine_mean5(a.cur, o, P, PP, tA);
+                fine_mean5(a.cur, o + 2, P, PP, tB);
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    vA[f] = tA[f];
+                    vB[f] = tB[f];
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    vA[f] = __ldg(a.cur.p[f] + o);
+                    vB[f] = __ldg(a.cur.p[f] + o + dB);
+                }
+            }
+        };
+
+        // ---- task prologue: boundary fluxes of plane 0 and the ghost plane below
+        double gzA[NV], gzB[NV];
+        bnd_issue(0);
+        cp_async_commit();
+        bnd_issue(1);
+        cp_async_commit();
+        zghost(0, gzA, gzB);
+        cp_async_wait<1>();
+        bnd_flux(0);
+        __syncwarp();
+
+        struct PlaneState
+        {
+            Cell3  A, B;               // records of the lane's two cells
+            double accA[NV], accB[NV]; // U + hx dFx + hy dFy - hz Fz(low)
+        };
+        PlaneState s0, s1;
+        // pair (padded x = x0 + 2 xq, +1) = (left cell | A) of the row being finished
+        size_t go = pb + (size_t)H * PP + (size_t)(H + y0 + yy) * P + x0 + 2 * xq;
+        int    sl = 0; // slot of the streamed plane inside its chunk
+
+        // finish a plane: add the upper z-face flux, store, wave speeds.  Whole padded rows (and
+        // the ghost rows of the plane) are stored; lane (y, xq) stores the 16-byte aligned pair
+        // (B of the left lane | A).
+        const bool edge_row = (yy == 0) || (yy == 7); // also writes the ghost row next to it
+        const int  edge_off = (yy == 0) ? -P : P;
+        auto finish = [&](const PlaneState& pv, const double (&GzA)[NV], const double (&GzB)[NV],
+                          bool fin) {
+            double rA[NV], rB[NV];
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                rA[f]        = fma(hz, GzA[f], pv.accA[f]);
+                rB[f]        = fma(hz, GzB[f], pv.accB[f]);
+                const double lft = __shfl_up_sync(0xffffffffu, rB[f], 1);
+                double*      rowp = a.nxt.p[f] + go;
+                if constexpr (C::NB == 1)
+                {
+                    // pair (left | A); the row's first lane writes the ghost column as a copy
+                    const double2 v = make_double2(xq == 0 ? rA[f] : lft, rA[f]);
+                    const double2 w = make_double2(rB[f], rB[f]);
+                    if (fin)
+                    {
+                        *reinterpret_cast<double2*>(rowp) = v;
+                        if (xq == 3) *reinterpret_cast<double2*>(rowp + 2) = w;
+                        if (edge_row)
+                        {
+                            *reinterpret_cast<double2*>(rowp + edge_off) = v;
+                            if (xq == 3) *reinterpret_cast<double2*>(rowp + edge_off + 2) = w;
+                        }
+                    }
+                }
+                else
+                {
+                    auto put = [&](double* q) {
+                        if (xq == 0)
+                        {
+                            if (bx == 0)
+                                *reinterpret_cast<double2*>(q) = make_double2(rA[f], rA[f]);
+                            else
+                                q[1] = rA[f];
+                        }
+                        else
+                            *reinterpret_cast<double2*>(q) = make_double2(lft, rA[f]);
+                        if (xq == 3)
+                        {
+                            if (bx == C::NBX - 1)
+                                *reinterpret_cast<double2*>(q + 2) = make_double2(rB[f], rB[f]);
+                            else
+                                q[2] = rB[f];
+                        }
+                    };
+                    if (fin)
+                    {
+                        put(rowp);
+                        if (yy == 0 && by == 0) put(rowp - P);
+                        if (yy == 7 && by == C::NBY - 1) put(rowp + P);
+                    }
+                }
+            }
+            if (fin) go += PP;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+            {
+                const double* n    = c2 ? rB : rA;
+                const double  irho = rcp_nr2(n[0]);
+                double        K    = n[1] * n[1];
+                K                  = fma(n[2], n[2], K);
+                K                  = fma(n[3], n[3], K);
+                K *= 0.5 * irho;
+                const double pr = gm1 * (n[4] - K);
+                const double cs = sqrt_nr2(g * pr * irho);
+                sxm             = fin ? pos_max(sxm, fabs(n[1] * irho) + cs) : sxm;
+                sym             = fin ? pos_max(sym, fabs(n[2] * irho) + cs) : sym;
+                szm             = fin ? pos_max(szm, fabs(n[3] * irho) + cs) : szm;
+            }
+        };
+
+        // one interior plane z: `pv` = state of plane z-1 (or of the ghost plane below), `nw` =
+        // state of plane z.  fin: plane z-1 exists and is finished here; last: z == S-1 (the
+        // ghost plane above is fetched instead of the next boundary faces).  ONE instance of this
+        // body exists in the kernel (rolled loop): it has to stay inside the instruction cache.
+        auto plane_step = [&](int z, const PlaneState& pv, PlaneState& nw, bool fin, bool last) {
+            const int BUF = z & 1;
+            if (z + 2 < S) bnd_issue(z + 2);
+            cp_async_commit();
+            if (last) zghost(1, gzA, gzB); // in flight during the last plane
+            if (sl == 0) mbar_wait(&bar[cst], cph);
+            const double* src = ring + cst * C::STAGE + sl * PLD + (C::ROW0 + yy) * P + x0 + 2 * xq;
+            double        Lu[NV];
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                const double2 v0 = *reinterpret_cast<const double2*>(src + f * FS);
+                Lu[f]            = v0.x;
+                nw.A.u[f]        = v0.y;
+                nw.B.u[f]        = src[f * FS + 2];
+            }
+            // boundary fluxes of the NEXT plane (its inputs were requested one plane ago) while
+            // the shared-memory reads of this plane are in flight
+            if (!last)
+            {
+                cp_async_wait<1>();
+                bnd_flux(z + 1);
+            }
+            prims3(nw.A, g, gm1);
+            prims3(nw.B, g, gm1);
+            double GzA[NV], GzB[NV];
+            flux3<2>(pv.A, nw.A, GzA);
+            flux3<2>(pv.B, nw.B, GzB);
+            finish(pv, GzA, GzB, fin);
+            const double* bfp = sBF + BUF * 32 * C::BFW;
+            // ---- x faces: L|A from the left lane's B record, A|B local, B|R = right lane's
+            // L|A; the row's first / last lane take the parked boundary fluxes
+            {
+                const double2* bf =
+                    reinterpret_cast<const double2*>(bfp + ((xq >> 1) * 8 + yy) * C::BFW);
+                const double2 b0 = bf[0], b1 = bf[1], b2 = bf[2];
+                const double  bfl[NV] = { b0.x, b0.y, b1.x, b1.y, b2.x };
+                Cell3         L;
+#pragma unroll
+                for (int f = 0; f < NV; ++f) L.u[f] = Lu[f];
+                L.p  = __shfl_up_sync(0xffffffffu, nw.B.p, 1);
+                L.a  = __shfl_up_sync(0xffffffffu, nw.B.a, 1);
+                L.ir = __shfl_up_sync(0xffffffffu, nw.B.ir, 1);
+                double GL[NV], GM[NV];
+                flux3<0>(L, nw.A, GL);
+                flux3<0>(nw.A, nw.B, GM);
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    if (xq == 0) GL[f] = bfl[f];
+                    double GR = __shfl_down_sync(0xffffffffu, GL[f], 1);
+                    if (xq == 3) GR = bfl[f];
+                    nw.accA[f] = fma(hx, GM[f] - GL[f], nw.A.u[f]);
+                    nw.accB[f] = fma(hx, GR - GM[f], nw.B.u[f]);
+                }
+            }
+            // ---- y faces: lower face from the record of lane-4 (U from the staged plane),
+            // upper face = lane+4's lower face; first / last row take the parked fluxes
+            {
+                const int yl = (C::ROW0 + yy > 0) ? -P : 0; // staged row below (clamped)
+                Cell3     YA, YB;
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    const double2 v0 = *reinterpret_cast<const double2*>(src + f * FS + yl);
+                    YA.u[f]          = v0.y;
+                    YB.u[f]          = src[f * FS + yl + 2];
+                }
+                YA.p  = __shfl_up_sync(0xffffffffu, nw.A.p, 4);
+                YA.a  = __shfl_up_sync(0xffffffffu, nw.A.a, 4);
+                YA.ir = __shfl_up_sync(0xffffffffu, nw.A.ir, 4);
+                YB.p  = __shfl_up_sync(0xffffffffu, nw.B.p, 4);
+                YB.a  = __shfl_up_sync(0xffffffffu, nw.B.a, 4);
+                YB.ir = __shfl_up_sync(0xffffffffu, nw.B.ir, 4);
+                double GyA[NV], GyB[NV];
+                flux3<1>(YA, nw.A, GyA);
+                flux3<1>(YB, nw.B, GyB);
+                const double2* bf = reinterpret_cast<const double2*>(
+                    bfp + ((2 + (yy >> 2)) * 8 + 2 * xq) * C::BFW);
+                const double2 c0 = bf[0], c1 = bf[1], c2 = bf[2], d0 = bf[3], d1 = bf[4], d2 = bf[5];
+                const double  bA[NV] = { c0.x, c0.y, c1.x, c1.y, c2.x };
+                const double  bB[NV] = { d0.x, d0.y, d1.x, d1.y, d2.x };
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    if (yy == 0)
+                    {
+                        GyA[f] = bA[f];
+                        GyB[f] = bB[f];
+                    }
+                    double upA = __shfl_down_sync(0xffffffffu, GyA[f], 4);
+                    double upB = __shfl_down_sync(0xffffffffu, GyB[f], 4);
+                    if (yy == 7)
+                    {
+                        upA = bA[f];
+                        upB = bB[f];
+                    }
+                    nw.accA[f] = fma(hy, upA - GyA[f], nw.accA[f]);
+                    nw.accB[f] = fma(hy, upB - GyB[f], nw.accB[f]);
+                }
+            }
+            // ---- lower z face
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                nw.accA[f] = fma(nhz, GzA[f], nw.accA[f]);
+                nw.accB[f] = fma(nhz, GzB[f], nw.accB[f]);
+            }
+            __syncwarp();
+            if (++sl == CR)
+            {
+                // every lane has consumed its values of this stage's last plane (see the 2D
+                // kernel): the stage can be refilled
+                sl = 0;
+                issue_next();
+                if (++cst == NS)
+                {
+                    cst = 0;
+                    cph ^= 1;
+                }
+            }
+        };
+        // ghost plane below -> records (accumulators: any finite values, never stored)
+#pragma unroll
+        for (int f = 0; f < NV; ++f)
+        {
+            s0.A.u[f] = s0.accA[f] = gzA[f];
+            s0.B.u[f] = s0.accB[f] = gzB[f];
+        }
+        prims3(s0.A, g, gm1);
+        prims3(s0.B, g, gm1);
+#pragma unroll 1
+        for (int z = 0; z < S; ++z)
+        {
+            plane_step(z, s0, s1, z > 0, z == S - 1);
+            s0 = s1;
+        }
+        // ghost plane above: z-face flux into plane S-1, finish it
+        {
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                s1.A.u[f] = gzA[f];
+                s1.B.u[f] = gzB[f];
+            }
+            prims3(s1.A, g, gm1);
+            prims3(s1.B, g, gm1);
+            double GzA[NV], GzB[NV];
+            flux3<2>(s0.A, s1.A, GzA);
+            flux3<2>(s0.B, s1.B, GzB);
+            finish(s0, GzA, GzB, true);
+        }
+        __syncwarp(); // sBF is rewritten by the next task
+    }
+
+    if (a.sc.dtmin_out != nullptr)
+    {
+        if (lvl_prev >= 0)
+        {
+            if (sxm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][0] / sxm);
+            if (sym > 1e-12) cand = fmin(cand, a.dx[lvl_prev][1] / sym);
+            if (szm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][2] / szm);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = fmin(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0 && nt > 0)
+            atomicMin(a.sc.dtmin_out, (unsigned long long)__double_as_longlong(cand));
+    }
+}
+
+} // namespace amrb

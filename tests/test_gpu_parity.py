@@ -57,7 +57,8 @@ def test_device_matches_reference_dump(amrb, name, mode):
 
 
 @pytest.mark.parametrize("cfgname,levels", [("r2_s64_h1_d7_euler", 2), ("r2_s32_h1_d7_adv", 2),
-                                            ("r3_s16_h1_d5_euler", 1), ("r3_s8_h1_d5_adv", 2),
+                                            ("r3_s16_h1_d5_euler", 1), ("r3_s8_h1_d5_euler", 2),
+                                            ("r3_s8_h1_d5_adv", 2),
                                             ("r2_s10_h2_d7_euler", 2)])
 def test_device_matches_oracle_on_bench_shapes(amrb, cfgname, levels):
     """Shapes without a committed reference dump (the 64x64 / 16^3 benchmark patches): compare with

@@ -141,6 +141,14 @@ int main()
     run<8, 4>(d, span, 1056, -38016, 0, 2, sink, 1);
     run<12, 4>(d, span, 1056, -38016, 0, 2, sink, 1);
     run<4, 4>(d, span, 1056, -38016, 0, 4, sink, 1);
+    printf("3D plane streams (region 8000 B = one 10^3 field-patch)\n");
+    run<3, 4>(d, span, 1600, -8000, 0, 2, sink);
+    run<4, 4>(d, span, 800, -8000, 0, 2, sink);
+    run<3, 4>(d, span, 800, -8000, 0, 3, sink);
+    run<2, 4>(d, span, 4000, -8000, 0, 2, sink);
+    run<2, 4>(d, span, 8000, -8000, 0, 2, sink);
+    run<3, 4>(d, span, 1600, -8000, 0, 2, sink, 1);
+    run<4, 4>(d, span, 1152, -46656, 0, 2, sink);
     printf("grid sweep\n");
     run<3, 4>(d, span, 1056, 1056, 0, 4, sink);
     run<6, 4>(d, span, 1056, 1056, 0, 2, sink);

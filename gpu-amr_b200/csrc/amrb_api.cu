@@ -376,6 +376,10 @@ void fill_step_args(const amrb_pool* p, StepArgs& a)
     a.list      = nullptr;
     a.n_patches = (int)p->n_owned;
     a.lazy_halo = (p->mode != 1) ? 1 : 0;
+    {
+        static const int tm = getenv("AMRB_TASKMAP") ? atoi(getenv("AMRB_TASKMAP")) : 1;
+        a.task_map = tm;
+    }
     a.gamma     = p->gamma;
     std::memcpy(a.dx, p->dx, sizeof(a.dx));
     a.sc = StepScalars{ nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, p->cfl };

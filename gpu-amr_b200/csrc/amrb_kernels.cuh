@@ -258,6 +258,9 @@ struct StepArgs
     const int32_t* list; // optional patch sub-list
     int            n_patches;
     int            lazy_halo; // 1: gather ghosts from neighbor interiors; 0: trust global halos
+    int            task_map;  // marching kernels: 1 = tasks interleaved over all warps of the grid
+                              // (the chip sweeps one Morton window at a time: ghost gathers hit L2),
+                              // 0 = contiguous task range per CTA
     double         gamma;
     double         dx[kMaxLevel + 1][3]; // per level, per solver direction (x,y,z)
     StepScalars    sc;

@@ -144,10 +144,12 @@ euler2d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     const int n_tasks = n_items * C::NB;
     const int tb      = (int)((long long)n_tasks * blockIdx.x / gridDim.x);
     const int te      = (int)((long long)n_tasks * (blockIdx.x + 1) / gridDim.x);
-    const int nt      = (te - tb > warp) ? (te - tb - warp + WPC - 1) / WPC : 0;
+    const int gw = blockIdx.x * WPC + warp, nw_all = gridDim.x * WPC; // warp of the grid
+    const int nt = a.task_map ? ((n_tasks > gw) ? (n_tasks - gw + nw_all - 1) / nw_all : 0)
+                              : ((te - tb > warp) ? (te - tb - warp + WPC - 1) / WPC : 0);
 
     auto task_of = [&](int k, int& p, int& r0) {
-        const int tau  = tb + warp + k * WPC;
+        const int tau  = a.task_map ? gw + k * nw_all : tb + warp + k * WPC;
         const int item = tau / C::NB;
         r0             = (tau % C::NB) * BAND;
         p              = a.list ? a.list[item] : item;

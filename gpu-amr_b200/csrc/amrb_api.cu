@@ -183,7 +183,16 @@ struct Inst
             const int band = (v == 1) ? 16 : (v == 2) ? 32 : (v == 3) ? 64 : pick_band(n_items);
             if (v != 10)
             {
-                if (band == 64)
+                // AMRB_RING: ring shape (rows per TMA copy / stages): a warp's bulk copies complete
+                // one at a time (~0.5 us each, tools/tma_bench.cu), so taller chunks = fewer waits
+                static const int ring = getenv("AMRB_RING") ? atoi(getenv("AMRB_RING")) : 0;
+                if (band == 64 && ring == 1)
+                    march<64, 3, 3, 4, 2>(st, a, n_items);
+                else if (band == 64 && ring == 2)
+                    march<64, 6, 2, 4, 2>(st, a, n_items);
+                else if (band == 64 && ring == 3)
+                    march<64, 3, 2, 4, 2>(st, a, n_items);
+                else if (band == 64)
                     march<64, 2, 3, 4, 2>(st, a, n_items);
                 else if (band == 32)
                     march<32, 2, 3, 4, 2>(st, a, n_items);
@@ -297,6 +306,7 @@ struct amrb_pool
     double*      h_dts       = nullptr; // pinned
     size_t       scal_cap = 0, batch_steps = 0, batch_k = 0;
     bool         batch_open = false, batch_pending = false, carry_valid = false;
+    bool         pending_in_graph = false; // the batch was enqueued under stream capture: no event
     bool         step_touched = false;
     cudaEvent_t  batch_done = nullptr;
     // staging
@@ -390,6 +400,18 @@ amrb_status check_launch(amrb_pool* p, const char* what)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     ++p->launches;
+    return AMRB_OK;
+}
+
+// wait for the batch enqueued last (amr_solver::wait_for_pending_dt_copy, amr_solver.hpp:416-466)
+amrb_status wait_batch(amrb_pool* p)
+{
+    if (p->pending_in_graph)
+        AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    else
+        AMRB_CUDA(cudaEventSynchronize(p->batch_done));
+    p->batch_pending    = false;
+    p->pending_in_graph = false;
     return AMRB_OK;
 }
 
@@ -851,8 +873,7 @@ amrb_status amrb_pool_batch_begin(amrb_pool* p, size_t max_steps, double remaini
     if (p->batch_pending)
     {
         // same as wait_for_pending_dt_copy() at the top of advance_batch_async (amr_solver.hpp:163)
-        AMRB_CUDA(cudaEventSynchronize(p->batch_done));
-        p->batch_pending = false;
+        AMRB_TRY(wait_batch(p));
     }
     const size_t last = p->batch_steps; // slot holding the dt-min of the state we start from
     const bool   carry = p->carry_valid && p->scal_cap >= max_steps + 2;
@@ -934,7 +955,12 @@ amrb_status amrb_pool_batch_end(amrb_pool* p, int materialise_halos)
     if (p->batch_k > 0)
         AMRB_CUDA(cudaMemcpyAsync(p->h_dts, p->d_dts, p->batch_k * sizeof(double),
                                   cudaMemcpyDeviceToHost, p->stream));
-    AMRB_CUDA(cudaEventRecord(p->batch_done, p->stream));
+    // Under stream capture (the caller records the batch into a CUDA graph) an event recorded here
+    // could not be waited for afterwards: the wait falls back to a stream synchronize.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    AMRB_CUDA(cudaStreamIsCapturing(p->stream, &cap));
+    p->pending_in_graph = (cap != cudaStreamCaptureStatusNone);
+    if (!p->pending_in_graph) AMRB_CUDA(cudaEventRecord(p->batch_done, p->stream));
     p->batch_open    = false;
     p->batch_pending = true;
     p->carry_valid   = true;
@@ -968,8 +994,7 @@ amrb_status amrb_pool_finish_advance_batch(amrb_pool* p, double* dt_sum, size_t*
     if (p->batch_pending)
     {
         AMRB_TRY(set_device(p));
-        AMRB_CUDA(cudaEventSynchronize(p->batch_done));
-        p->batch_pending = false;
+        AMRB_TRY(wait_batch(p));
     }
     // accumulate exactly like finalize_step_dt_kernel: acc += step_dt in step order, count the
     // steps with dt > 0 (src/cuda/fvm_time_step.cu:224-230)

@@ -156,7 +156,7 @@ struct March3Cfg
     static constexpr int RING  = NS * STAGE;
     static constexpr int BFW   = 6;                    // doubles per parked boundary flux (5 + pad)
     static constexpr int BF    = 2 * 32 * BFW;         // double-buffered, 32 faces per plane
-    static constexpr int ST    = 2 * 10 * 32;          // boundary-face inputs in flight: [2][10][32]
+    static constexpr int ST    = 10 * 32;              // boundary-face inputs in flight: [10][32]
     static constexpr int WARP_DOUBLES = RING + BF + ST;
     static constexpr size_t SMEM      = (size_t)WPC * WARP_DOUBLES * sizeof(double);
     static_assert(S % 8 == 0 && S % 2 == 0, "8 x 8 column blocks");
@@ -356,7 +356,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         // issue the loads of this lane's boundary face of plane z (ghost + interior cell, all
         // fields) into staging buffer z & 1; they land asynchronously (cp.async group)
         auto bnd_issue = [&](int z) {
-            double* st = sST + (z & 1) * 320;
+            double* st = sST;
             if (gs.finer)
             {
                 const size_t o = (size_t)(z < S / 2 ? gs.q0 : gs.q1) * G::FLAT +
@@ -383,7 +383,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         // left cell), so one branch-free evaluation serves all four sides.
         const double bsgn = (side & 1) ? -1.0 : 1.0;
         auto bnd_flux = [&](int z) {
-            const double* st = sST + (z & 1) * 320;
+            const double* st = sST;
             Cell3         gc, ic_;
 #pragma unroll
             for (int f = 0; f < NV; ++f)
@@ -468,10 +468,8 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         double gzA[NV], gzB[NV];
         bnd_issue(0);
         cp_async_commit();
-        bnd_issue(1);
-        cp_async_commit();
         zghost(0, gzA, gzB);
-        cp_async_wait<1>();
+        cp_async_wait<0>();
         bnd_flux(0);
         __syncwarp();
 
@@ -568,9 +566,16 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         // body exists in the kernel (rolled loop): it has to stay inside the instruction cache.
         auto plane_step = [&](int z, const PlaneState& pv, PlaneState& nw, bool fin, bool last) {
             const int BUF = z & 1;
-            if (z + 2 < S) bnd_issue(z + 2);
-            cp_async_commit();
-            if (last) zghost(1, gzA, gzB); // in flight during the last plane
+            // inputs of the next plane's boundary faces: requested now, used at the end of this
+            // step.  (One plane of lead, not more: the neighbor patches are streamed by warps
+            // running in lock-step with this one, a later request finds their planes in L2.)
+            if (!last)
+            {
+                bnd_issue(z + 1);
+                cp_async_commit();
+            }
+            else
+                zghost(1, gzA, gzB); // in flight during the last plane
             if (sl == 0) mbar_wait(&bar[cst], cph);
             const double* src = ring + cst * C::STAGE + sl * PLD + (C::ROW0 + yy) * P + x0 + 2 * xq;
             double        Lu[NV];
@@ -581,13 +586,6 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
                 Lu[f]            = v0.x;
                 nw.A.u[f]        = v0.y;
                 nw.B.u[f]        = src[f * FS + 2];
-            }
-            // boundary fluxes of the NEXT plane (its inputs were requested one plane ago) while
-            // the shared-memory reads of this plane are in flight
-            if (!last)
-            {
-                cp_async_wait<1>();
-                bnd_flux(z + 1);
             }
             prims3(nw.A, g, gm1);
             prims3(nw.B, g, gm1);
@@ -673,6 +671,11 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
             {
                 nw.accA[f] = fma(nhz, GzA[f], nw.accA[f]);
                 nw.accB[f] = fma(nhz, GzB[f], nw.accB[f]);
+            }
+            if (!last)
+            {
+                cp_async_wait<0>();
+                bnd_flux(z + 1);
             }
             __syncwarp();
             if (++sl == CR)

@@ -99,6 +99,14 @@ class ShardedSolver:
         self.stream = torch.cuda.ExternalStream(int(self.L.amrb_pool_stream(self.pool.h) or 0),
                                                 device=device)
         self.comm_stream = torch.cuda.Stream(device=device)
+        # the CFL all-reduce runs on its own stream and its own communicator, so that it overlaps
+        # the next step's slab exchange instead of sitting between two steps
+        self.ar_stream = torch.cuda.Stream(device=device)
+        self.ar_group = None
+        if world > 1 and dist.get_backend() == "nccl" and os.environ.get("AMRB_AR_GROUP", "1") != "0":
+            self.ar_group = dist.new_group(ranks=list(range(world)))
+        self.graphs = {}
+        self._dtmin_cache = {}
         slab = self.L.amrb_pool_face_slab_doubles(self.pool.h, 0) * cfg.nvar
         self.slab = slab
         dev = torch.device("cuda", device)
@@ -158,20 +166,34 @@ class ShardedSolver:
         self.launches += 1
 
     # ---- stepping
+    def _dtmin_tensor(self, k):
+        t = self._dtmin_cache.get(k)
+        if t is None:
+            t = raw_tensor(self.L.amrb_pool_dtmin_slot(self.pool.h, k), 1, self.torch)
+            self._dtmin_cache[k] = t
+        return t
+
     def _allreduce_dtmin(self, k):
+        """global CFL minimum of the state entering step k (one double), on the side stream;
+        the step kernels of step k wait for it, the slab exchange of step k does not"""
         torch, dist = self.torch, self.dist
-        ptr = self.L.amrb_pool_dtmin_slot(self.pool.h, k)
-        t = raw_tensor(ptr, 1, torch)
-        with torch.cuda.stream(self.stream):
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        t = self._dtmin_tensor(k)
+        self.ar_stream.wait_stream(self.stream)
+        with torch.cuda.stream(self.ar_stream):
+            if self.ar_group is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.ar_group)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
 
     def advance_batch_async(self, steps, remaining=B.DBL_MAX, overlap=True):
         L, h, pl = self.L, self.pool.h, self.plan
         B.check(L.amrb_pool_batch_begin(h, steps, remaining))
+        self._dtmin_cache = {} if len(self._dtmin_cache) > 4096 else self._dtmin_cache
         self._allreduce_dtmin(0)
         for k in range(steps):
             self._pack()
             self._comm()
+            self.stream.wait_stream(self.ar_stream)          # dt of this step is global now
             if overlap and len(pl.interior):
                 B.check(L.amrb_pool_step_partial(h, self.d_interior.data_ptr(), len(pl.interior)))
                 self.launches += 1
@@ -186,9 +208,35 @@ class ShardedSolver:
                 self.launches += 1
             self._allreduce_dtmin(k + 1)
             B.check(L.amrb_pool_step_commit(h))
+        self.stream.wait_stream(self.ar_stream)
         self.exchange()
         B.check(L.amrb_pool_batch_end(h, 1))
         self.launches += 1
+
+    def advance_batch_graph(self, steps, overlap=True):
+        """Same batch, recorded once into a CUDA graph (kernels, NCCL exchanges and the event
+        fork/joins between the three streams) and replayed: no per-launch host work inside the
+        batch.  Needs an even step count (the current/next buffer pointers of the recorded
+        launches must be back in place after one replay) and a preceding eager batch of the same
+        length (allocations, carried dt-min slot)."""
+        torch = self.torch
+        if steps % 2 != 0:
+            raise ValueError("graph replay needs an even number of steps")
+        g = self.graphs.get((steps, overlap))
+        if g is None:
+            self.finish_advance_batch()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = self.launches
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                self.advance_batch_async(steps, overlap=overlap)
+            self.graph_launches = self.launches - l0
+            self.launches = l0
+            self.finish_advance_batch()                      # host state only: nothing ran yet
+            self.graphs[(steps, overlap)] = g
+        with torch.cuda.stream(self.stream):
+            g.replay()
+        self.launches += self.graph_launches
 
     def finish_advance_batch(self, max_steps=0):
         return self.pool.finish_advance_batch(max_steps)
@@ -252,6 +300,42 @@ def run_bench(args, METRIC, UNIT):
     sol.finish_advance_batch()
     sol.advance_batch_async(K)
     sol.finish_advance_batch()
+    # exchange schedule: (a) interior patches advance while the slabs travel, boundary patches after
+    # the receive (two step launches), or (b) exchange first, then one step launch over all patches.
+    # (a) wins when a rank's share is large, (b) when it is small (a launch over few boundary
+    # patches still costs a full pipeline fill); picked here by timing a short batch of each.
+    mode_ms = {}
+    for ov in (True, False):
+        for rep in range(2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(sol.stream)
+            sol.advance_batch_async(10, overlap=ov)
+            e1.record(sol.stream)
+            torch.cuda.synchronize()
+            sol.finish_advance_batch()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mode_ms[ov] = float(t.item())
+    overlap = mode_ms[True] <= mode_ms[False]
+    if os.environ.get("AMRB_OVERLAP"):
+        overlap = os.environ["AMRB_OVERLAP"] != "0"
+    # AMRB_GRAPH=1: the timed batches replay a CUDA graph of the K-step batch (K even)
+    use_graph = (K % 2 == 0) and os.environ.get("AMRB_GRAPH", "0") == "1"
+    if use_graph:
+        try:
+            sol.advance_batch_graph(K, overlap)              # records, then one untimed replay
+            torch.cuda.synchronize()
+            sol.finish_advance_batch()
+        except Exception as e:                               # noqa: BLE001 - report and fall back
+            sys.stderr.write("rank %d: graph capture failed (%r), eager launches instead\n" % (rank, e))
+            use_graph = False
+    flag = torch.tensor([1 if use_graph else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    use_graph = bool(int(flag.item()))
+    advance = (lambda k: sol.advance_batch_graph(k, overlap)) if use_graph else \
+        (lambda k: sol.advance_batch_async(k, overlap=overlap))
 
     clocks = bench_mod.ClockSampler(local)
     if rank == 0:
@@ -266,7 +350,7 @@ def run_bench(args, METRIC, UNIT):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(sol.stream)
-        sol.advance_batch_async(K)
+        advance(K)
         e1.record(sol.stream)
         torch.cuda.synchronize()
         dt_sum, executed, _ = sol.finish_advance_batch()
@@ -293,7 +377,7 @@ def run_bench(args, METRIC, UNIT):
         B.check(L.amrb_copy_host_to_device_async(L.amrb_pool_field(sol.pool.h, f), pinned[f].data_ptr(),
                                                  n_own * sol.pool.flat * 8, L.amrb_pool_stream(sol.pool.h)))
     sol.halo_exchange()
-    sol.advance_batch_async(K)
+    sol.advance_batch_async(K, overlap=overlap)              # eager: the state was just replaced
     for f in range(cfg.nvar):
         B.check(L.amrb_copy_device_to_host_async(pinned[f].data_ptr(), L.amrb_pool_field(sol.pool.h, f),
                                                  n_own * sol.pool.flat * 8, L.amrb_pool_stream(sol.pool.h)))
@@ -319,7 +403,11 @@ def run_bench(args, METRIC, UNIT):
                                    "partition over %d GPUs" % (base, radius, world),
                        "cells": int(cells), "patches": int(P), "cells_per_gpu": int(cells // world),
                        "l2_policy": "inputs larger than L2 (0.8 GB of state per GPU vs 126 MB)",
-                       "executed_steps": int(executed), "ghost_patches_rank0": int(len(sol.plan.ghost_global)),
+                       "executed_steps": int(executed), "launch_mode": "cuda graph replay of the K-step batch"
+                       if use_graph else "eager launches",
+                       "exchange_schedule": "interior patches overlap the slab exchange" if overlap else
+                       "exchange, then one launch over all patches",
+                       "schedule_probe_ms_per_10_steps": {"overlap": mode_ms[True], "single_launch": mode_ms[False]}, "ghost_patches_rank0": int(len(sol.plan.ghost_global)),
                        "ghost_bytes_per_step_all_ranks": float(tot[1].item())},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": bench_mod.load_traffic(),
@@ -333,5 +421,10 @@ def run_bench(args, METRIC, UNIT):
         }
         print(json.dumps(line))
     dist.barrier()
+    if use_graph:
+        sol.graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
     sol.pool.close()
     dist.destroy_process_group()

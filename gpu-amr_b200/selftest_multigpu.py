@@ -34,6 +34,16 @@ def main():
     for overlap in (True, False):
         sol.advance_batch_async(steps, overlap=overlap)
         acc, n, dts = sol.finish_advance_batch(steps)
+    # optionally: the same batch recorded into a CUDA graph and replayed (even step count)
+    use_graph = os.environ.get("AMRB_SELFTEST_GRAPH", "0") == "1"
+    sol.advance_batch_async(6)
+    sol.finish_advance_batch(6)
+    if use_graph:
+        sol.advance_batch_graph(6)
+        torch.cuda.synchronize()
+    else:
+        sol.advance_batch_async(6, overlap=False)
+    acc, n, dts = sol.finish_advance_batch(6)
     mine = sol.download_interior()
     halo = np.stack([sol.pool.download(f, sol.plan.n_owned) for f in range(cfg.nvar)])
     gathered = [None] * world
@@ -48,9 +58,9 @@ def main():
         for f in range(cfg.nvar):
             pool.upload_interior(f, ic[f])
         pool.halo_exchange()
-        for _ in range(2):
-            pool.advance_batch_async(steps)
-            acc1, n1, _ = pool.finish_advance_batch(steps)
+        for st in (steps, steps, 6, 6):
+            pool.advance_batch_async(st)
+            acc1, n1, _ = pool.finish_advance_batch(st)
         ref = np.stack([pool.download_interior(f, len(ids)) for f in range(cfg.nvar)])
         refh = np.stack([pool.download(f, len(ids)) for f in range(cfg.nvar)])
         got = np.concatenate([g[0].reshape(cfg.nvar, -1, cfg.data) for g in gathered], axis=1)
@@ -67,9 +77,16 @@ def main():
         pool.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
+    rc = 0 if int(flag.item()) == 1 else 1
+    if use_graph:
+        # a process group whose NCCL kernels live in a recorded graph does not tear down cleanly
+        sol.graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(rc)
     sol.pool.close()
     dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@
 #include "patch.hpp"
 #include "patch_layout.hpp"
 #include "patch_utils.hpp"
+#include "utility/logging.hpp"
 
 #include <array>
 #include <cstdint>

@@ -16,13 +16,13 @@ namespace amr::cell
         static constexpr auto index() noexcept -> std::size_t { return INDEX; }                  \
         static constexpr auto name() noexcept -> std::string_view { return LABEL; }              \
     };
-AMRB_FIELD(Rho, 0, "rho")
-AMRB_FIELD(Rhou, 1, "rhou")
-AMRB_FIELD(Rhov, 2, "rhov")
-AMRB_FIELD(Rhow, 3, "rhow")
-AMRB_FIELD(E2D, 3, "E")
-AMRB_FIELD(E3D, 4, "E")
-AMRB_FIELD(Scalar, 0, "scalar")
+AMRB_FIELD(Rho, 0, "Rho")
+AMRB_FIELD(Rhou, 1, "Rhou")
+AMRB_FIELD(Rhov, 2, "Rhov")
+AMRB_FIELD(Rhow, 3, "Rhow")
+AMRB_FIELD(E2D, 3, "E2D")
+AMRB_FIELD(E3D, 4, "E3D")
+AMRB_FIELD(Scalar, 0, "Scalar")
 #undef AMRB_FIELD
 
 struct EulerCell2D

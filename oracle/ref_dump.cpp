@@ -33,6 +33,7 @@
 //   I                      solver.initialize(IC) (pulse / gaussian, see ic())
 //   S n                    n x advance(); dt of every step recorded
 //   T n                    time n x advance() and print one JSON line (updates/s)
+//   V name                 vtk_print(tree) -> vtk_output/<name>.vtk in the working directory
 //   D tag                  dump ids, neighbor tables, padded data, under "tag/"
 // Output (argv[2]): flat sequence of records
 //   u32 name_len | name | u32 dtype(0=f64,1=i64,2=i32,3=i8,4=u64) | u32 ndim | u64 shape[ndim] | raw data
@@ -44,6 +45,7 @@
 #include "ndtree/intergrid_operator.hpp"
 #include "ndtree/ndtree.hpp"
 #include "ndtree/patch_layout.hpp"
+#include "ndtree/vtk_print.hpp"
 #include "solver/AdvectionPhysics.hpp"
 #include "solver/EulerPhysics.hpp"
 #include "solver/amr_solver.hpp"
@@ -424,6 +426,14 @@ int main(int argc, char** argv)
                 updates / el.count(), sum_dt
             );
             std::fflush(stdout);
+        }
+        else if (op == "V")
+        {
+            // the reference's own VTK writer over the current tree -> vtk_output/<name>.vtk (cwd)
+            std::string name;
+            is >> name;
+            amr::ndt::print::vtk_print<physics_t> printer(name);
+            printer.print(tree, ".vtk");
         }
         else if (op == "D")
         {

@@ -301,6 +301,7 @@ struct amrb_pool
     double       dx[kMaxLevel + 1][3]{};
     // batch scalars
     unsigned long long* d_dtmin = nullptr;
+    unsigned int*       d_queue = nullptr; // dynamic task counter of the 3D marching kernel
     double*      d_remaining = nullptr;
     double*      d_dts       = nullptr;
     double*      h_dts       = nullptr; // pinned
@@ -390,6 +391,8 @@ void fill_step_args(const amrb_pool* p, StepArgs& a)
         static const int tm = getenv("AMRB_TASKMAP") ? atoi(getenv("AMRB_TASKMAP")) : 1;
         a.task_map = tm;
     }
+    a.queue       = nullptr;
+    a.queue_reset = nullptr;
     a.gamma     = p->gamma;
     std::memcpy(a.dx, p->dx, sizeof(a.dx));
     a.sc = StepScalars{ nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, p->cfl };
@@ -652,6 +655,7 @@ amrb_status amrb_pool_destroy(amrb_pool* p)
     cudaFree(p->d_meta);
     cudaFree(p->d_level);
     cudaFree(p->d_dtmin);
+    if (p->d_queue) cudaFree(p->d_queue);
     cudaFree(p->d_remaining);
     cudaFree(p->d_dts);
     cudaFree(p->d_stage);
@@ -922,6 +926,15 @@ amrb_status amrb_pool_step_partial(amrb_pool* p, const int32_t* dev_list, size_t
     const int n_items = dev_list ? (int)count : (int)p->n_owned;
     if (n_items > 0)
     {
+        // 3D Euler (plane-marching kernel): tasks beyond the first of each warp are drawn from a
+        // device counter, zeroed in stream order before the launch (AMRB_QUEUE=0: static map)
+        static const int use_queue = getenv("AMRB_QUEUE") ? atoi(getenv("AMRB_QUEUE")) : 1;
+        if (use_queue && p->mode == 0 && p->lay.rank == 3 && p->lay.equation == AMRB_EQ_EULER)
+        {
+            if (!p->d_queue) AMRB_CUDA(cudaMalloc(&p->d_queue, sizeof(unsigned int)));
+            AMRB_CUDA(cudaMemsetAsync(p->d_queue, 0, sizeof(unsigned int), p->stream));
+            a.queue = p->d_queue;
+        }
         (p->mode == 2 ? p->ops->step_v1 : p->ops->step)(p->stream, a, n_items);
         AMRB_TRY(check_launch(p, "step_kernel"));
     }

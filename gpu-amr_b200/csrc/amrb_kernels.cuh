@@ -261,6 +261,10 @@ struct StepArgs
     int            task_map;  // marching kernels: 1 = tasks interleaved over all warps of the grid
                               // (the chip sweeps one Morton window at a time: ghost gathers hit L2),
                               // 0 = contiguous task range per CTA
+    unsigned int*  queue;       // optional dynamic task counter of THIS launch (3D marching kernel):
+                                // a warp takes its next task when it finishes one, so warps slowed
+                                // down by coarse/fine faces do not drift out of the common window
+    unsigned int*  queue_reset; // unused (the host zeroes the counter in stream order)
     double         gamma;
     double         dx[kMaxLevel + 1][3]; // per level, per solver direction (x,y,z)
     StepScalars    sc;

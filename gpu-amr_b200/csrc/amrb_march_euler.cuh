@@ -220,21 +220,61 @@ euler2d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         const size_t pb   = (size_t)p * G::FLAT;
         const bool   bot  = (r0 == 0), top = (r0 + BAND == S);
 
+        // ---- halo tables of the task's patch, hoisted: 4 relation bytes and 8 neighbor indices in
+        // three independent vector loads.  (Looked up per gather they made every ghost a chain of
+        // three dependent global loads -- relation, index, value -- and 20 % of all stall samples.)
+        const uint32_t mb = __ldg(reinterpret_cast<const uint32_t*>(a.meta) + p);
+        const int4     nA = __ldg(reinterpret_cast<const int4*>(a.nbr) + 2 * (size_t)p);
+        const int4     nB = __ldg(reinterpret_cast<const int4*>(a.nbr) + 2 * (size_t)p + 1);
+
         // ---- ghost value of padded cell (row, col) across face d, or the stored ghost when the
-        // tables say "none" / the caller asked to trust materialised halos
+        // tables say "none" / the caller asked to trust materialised halos.  Same index arithmetic
+        // as halo_source<2, S, H> (amrb_kernels.cuh), resolved once for all fields.
         auto ghost = [&](int d, int row, int col, double (&v)[NV]) {
-            const int      m  = a.meta[(size_t)p * G::NDIR + d];
-            const int32_t* nb = a.nbr + ((size_t)p * G::NDIR + d) * G::KF;
-            const int      idx[2] = { row, col };
-            if (a.lazy_halo && (m & 3) != 0)
+            const int m   = (int)((mb >> (8 * d)) & 0xffu);
+            const int rel = a.lazy_halo ? (m & 3) : 0;
+            const int n0  = (d == 0) ? nA.x : (d == 1) ? nA.z : (d == 2) ? nB.x : nB.z;
+            const int n1  = (d == 0) ? nA.y : (d == 1) ? nA.w : (d == 2) ? nB.y : nB.w;
+            int       fr = row, fc = col; // mirrored into the neighbor's frame
+            if ((d >> 1) == 0)
+                fr += (d & 1) ? -S : S;
+            else
+                fc += (d & 1) ? -S : S;
+            size_t o   = pb + (size_t)(row * P + col);
+            bool   fin = false;
+            if (rel == 1)
+                o = (size_t)n0 * G::FLAT + (size_t)(fr * P + fc);
+            else if (rel == 3)
+                o = (size_t)n0 * G::FLAT +
+                    (size_t)((H + ((m >> 2) & 1) * (S / 2) + (fr - H) / 2) * P +
+                             (H + ((m >> 3) & 1) * (S / 2) + (fc - H) / 2));
+            else if (rel == 2)
+            {
+                const int t = (((d >> 1) == 0) ? (col - H) : (row - H)) / (S / 2);
+                o   = (size_t)(t ? n1 : n0) * G::FLAT +
+                    (size_t)(((((fr - H) * 2) % S) + H) * P + (((fc - H) * 2) % S) + H);
+                fin = true;
+            }
+            if (!fin)
             {
 #pragma unroll
-                for (int f = 0; f < NV; ++f) v[f] = halo_source<2, S, H>(a.cur.p[f], nb, m, d, idx);
+                for (int f = 0; f < NV; ++f) v[f] = __ldg(a.cur.p[f] + o);
             }
             else
             {
+                // restriction: mean of the 2 x 2 fine cells, summed last-dim-fastest
+                // (patch_utils.hpp:203-234, intergrid_operator.hpp:92-106)
 #pragma unroll
-                for (int f = 0; f < NV; ++f) v[f] = __ldg(a.cur.p[f] + pb + row * P + col);
+                for (int f = 0; f < NV; ++f)
+                {
+                    const double* sp  = a.cur.p[f] + o;
+                    double        sum = 0.0;
+                    sum += __ldg(sp);
+                    sum += __ldg(sp + 1);
+                    sum += __ldg(sp + P);
+                    sum += __ldg(sp + P + 1);
+                    v[f] = sum / 4.0;
+                }
             }
         };
 

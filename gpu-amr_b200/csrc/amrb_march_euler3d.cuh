@@ -162,6 +162,7 @@ struct March3Cfg
     static_assert(S % 8 == 0 && S % 2 == 0, "8 x 8 column blocks");
     static_assert(H == 1, "odd ghost width: (ghost|first) and (second|right) pairs are 16-byte aligned");
     static_assert(S % CR == 0, "chunk shape");
+    static_assert(NS * CR <= S, "the ring never reaches beyond the next task");
     static_assert((PLD * 8) % 16 == 0 && (WARP_DOUBLES * 8) % 16 == 0, "bulk copy alignment");
 };
 
@@ -189,16 +190,24 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     double*   sST  = sBF + C::BF + lane; // this lane's column of the staging buffer
     uint64_t* bar  = bars + warp * NS;
 
-    // ---- this warp's tasks: the CTA owns a contiguous task range, its warps interleave
+    // ---- this warp's tasks.  Static map: warp gw of nw_all takes tasks gw, gw + nw_all, ...  (the chip
+    // sweeps one Morton window at a time).  With a.queue the first task is still gw, every further one
+    // is drawn from a device counter when the previous one is finished: the window stays tight even
+    // when tasks differ in cost (coarse/fine faces), which keeps the ghost gathers in L2.
     const int n_tasks = n_items * C::NB;
-    const int tb      = (int)((long long)n_tasks * blockIdx.x / gridDim.x);
-    const int te      = (int)((long long)n_tasks * (blockIdx.x + 1) / gridDim.x);
     const int gw = blockIdx.x * WPC + warp, nw_all = gridDim.x * WPC; // warp of the grid
-    const int nt = a.task_map ? ((n_tasks > gw) ? (n_tasks - gw + nw_all - 1) / nw_all : 0)
-                              : ((te - tb > warp) ? (te - tb - warp + WPC - 1) / WPC : 0);
+    auto next_tau = [&](int prev) -> int {
+        if (a.queue == nullptr) return prev + nw_all;
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(a.queue, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        return (t < 0x40000000u) ? nw_all + (int)t : n_tasks;
+    };
+    int tau_cur = (gw < n_tasks) ? gw : n_tasks; // n_tasks = "none"
+    int tau_nxt = (tau_cur < n_tasks) ? next_tau(tau_cur) : n_tasks;
+    int kc      = 0;                             // sequence number of the current task
 
-    auto task_of = [&](int k, int& p, int& bx, int& by) {
-        const int tau  = a.task_map ? gw + k * nw_all : tb + warp + k * WPC;
+    auto task_at = [&](int tau, int& p, int& bx, int& by) {
         const int item = tau / C::NB;
         const int blk  = tau % C::NB;
         bx             = blk % C::NBX;
@@ -216,9 +225,11 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     // ---- producer side of the ring (lane 0 issues; all lanes track the counters)
     int  ik = 0, ic = 0, ist = 0; // next chunk to issue: task, chunk in task, stage
     auto issue_next = [&]() {
-        if (ik >= nt) return;
+        // the producer is at most NS chunks ahead: inside the current task or the next one
+        const int tau = (ik == kc) ? tau_cur : tau_nxt;
+        if (tau >= n_tasks) return;
         int p, bx, by;
-        task_of(ik, p, bx, by);
+        task_at(tau, p, bx, by);
         if (lane == 0)
         {
             double* dst = ring + ist * C::STAGE;
@@ -267,10 +278,10 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
 
     int cst = 0, cph = 0; // consumer: stage and phase parity of the next chunk to wait for
 
-    for (int k = 0; k < nt; ++k)
+    while (tau_cur < n_tasks)
     {
         int p, bx, by;
-        task_of(k, p, bx, by);
+        task_at(tau_cur, p, bx, by);
         const int lvl = a.level[p];
         if (lvl != lvl_prev && lvl_prev >= 0)
         {
@@ -311,9 +322,10 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         const int ioff = i_y * P + i_x;
         GhostSrc3 gs;
         {
-            const int bm  = a.meta[(size_t)p * G::NDIR + bd];
-            const int rel = (!internal && a.lazy_halo) ? (bm & 3) : 0;
-            const int32_t* bnb = a.nbr + ((size_t)p * G::NDIR + bd) * G::KF;
+            // relation byte and the four neighbor indices of the side in two independent loads
+            const int  bm  = a.meta[(size_t)p * G::NDIR + bd];
+            const int4 bnb = __ldg(reinterpret_cast<const int4*>(a.nbr) + (size_t)p * G::NDIR + bd);
+            const int  rel = (!internal && a.lazy_halo) ? (bm & 3) : 0;
             int f_y = g_y, f_x = g_x; // mirrored into the neighbor's frame (patch_utils.hpp:322-327)
             if (side < 2)
                 f_x += (side & 1) ? -S : S;
@@ -330,14 +342,14 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
             }
             else if (rel == 1)
             {
-                gs.q0 = gs.q1 = bnb[0]; // same_t (patch_utils.hpp:315-332)
+                gs.q0 = gs.q1 = bnb.x; // same_t (patch_utils.hpp:315-332)
                 gs.off        = f_y * P + f_x;
             }
             else if (rel == 3)
             {
                 // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
                 const int qz = (bm >> 2) & 1, qy = (bm >> 3) & 1, qx = (bm >> 4) & 1;
-                gs.q0 = gs.q1 = bnb[0];
+                gs.q0 = gs.q1 = bnb.x;
                 gs.off = (H + qy * (S / 2) + (f_y - H) / 2) * P + (H + qx * (S / 2) + (f_x - H) / 2);
                 gs.zbase  = H + qz * (S / 2);
                 gs.zshift = 1;
@@ -347,8 +359,8 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
                 // finer_t: mean of 8 fine cells (patch_utils.hpp:334-386); finer-neighbor index =
                 // z half (bit 0) + 2 x half along the other tangential dim (neighbor.hpp:316-337)
                 const int t = ((side < 2) ? (g_y - H) : (g_x - H)) / (S / 2);
-                gs.q0       = bnb[2 * t];
-                gs.q1       = bnb[2 * t + 1];
+                gs.q0       = t ? bnb.z : bnb.x;
+                gs.q1       = t ? bnb.w : bnb.y;
                 gs.off      = ((((f_y - H) * 2) % S) + H) * P + (((f_x - H) * 2) % S) + H;
                 gs.finer    = 1;
             }
@@ -412,29 +424,30 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         };
         // ghost cells of this lane's column pair across the z faces (d = 0 below, 1 above)
         auto zghost = [&](int d, double (&vA)[NV], double (&vB)[NV]) {
-            const int      m   = a.meta[(size_t)p * G::NDIR + d];
-            const int32_t* nb  = a.nbr + ((size_t)p * G::NDIR + d) * G::KF;
-            const int      rel = a.lazy_halo ? (m & 3) : 0;
+            const int  m   = a.meta[(size_t)p * G::NDIR + d];
+            const int4 nb  = __ldg(reinterpret_cast<const int4*>(a.nbr) + (size_t)p * G::NDIR + d);
+            const int  rel = a.lazy_halo ? (m & 3) : 0;
             const int      y = H + y0 + yy, x = H + x0 + 2 * xq;
             const int      zi = d ? H + S : H - 1, zf = d ? H : H + S - 1; // ghost plane, mirrored
             int            q = p, dB = 1, fin = 0;
             int            off = zi * PP + y * P + x;
             if (rel == 1)
             {
-                q   = nb[0];
+                q   = nb.x;
                 off = zf * PP + y * P + x;
             }
             else if (rel == 3)
             {
                 const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
-                q   = nb[0];
+                q   = nb.x;
                 off = (H + qz * (S / 2) + (zf - H) / 2) * PP + (H + qy * (S / 2) + (y - H) / 2) * P +
                       (H + qx * (S / 2) + (x - H) / 2);
                 dB = 0;
             }
             else if (rel == 2)
             {
-                q   = nb[(y - H) / (S / 2) + 2 * ((x - H) / (S / 2))];
+                const int fi = (y - H) / (S / 2) + 2 * ((x - H) / (S / 2));
+                q            = (fi == 0) ? nb.x : (fi == 1) ? nb.y : (fi == 2) ? nb.z : nb.w;
                 off = ((((zf - H) * 2) % S) + H) * PP + ((((y - H) * 2) % S) + H) * P +
                       (((x - H) * 2) % S) + H;
                 dB  = 2;
@@ -722,6 +735,9 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
             finish(s0, GzA, GzB, true);
         }
         __syncwarp(); // sBF is rewritten by the next task
+        ++kc;
+        tau_cur = tau_nxt;
+        if (tau_cur < n_tasks) tau_nxt = next_tau(tau_cur);
     }
 
     if (a.sc.dtmin_out != nullptr)
@@ -734,7 +750,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cand = fmin(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-        if (lane == 0 && nt > 0)
+        if (lane == 0 && kc > 0)
             atomicMin(a.sc.dtmin_out, (unsigned long long)__double_as_longlong(cand));
     }
 }

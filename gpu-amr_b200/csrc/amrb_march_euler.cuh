@@ -202,11 +202,35 @@ euler2d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
 
     int cst = 0, cph = 0; // consumer: stage and phase parity of the next chunk to wait for
 
+    // halo tables of a task's patch, one 32-bit piece per lane (lanes 0-7: the 4 x 2 neighbor indices,
+    // lane 8: the 4 relation bytes, lane 9: level): loaded for the NEXT task while the current one is
+    // marched and handed round by shuffles, so that no task starts with a table lookup
+    auto tab_load = [&](int k) -> int {
+        int q, r;
+        task_of(k, q, r);
+        if (lane < 8) return __ldg(a.nbr + (size_t)q * 8 + lane);
+        if (lane == 8) return (int)__ldg(reinterpret_cast<const uint32_t*>(a.meta) + q);
+        if (lane == 9) return __ldg(a.level + q);
+        return 0;
+    };
+    int tab = (nt > 0) ? tab_load(0) : 0;
+
     for (int k = 0; k < nt; ++k)
     {
         int p, r0;
         task_of(k, p, r0);
-        const int lvl = a.level[p];
+        const int      lvl = __shfl_sync(0xffffffffu, tab, 9);
+        const uint32_t mb  = (uint32_t)__shfl_sync(0xffffffffu, tab, 8);
+        int4           nA, nB;
+        nA.x = __shfl_sync(0xffffffffu, tab, 0);
+        nA.y = __shfl_sync(0xffffffffu, tab, 1);
+        nA.z = __shfl_sync(0xffffffffu, tab, 2);
+        nA.w = __shfl_sync(0xffffffffu, tab, 3);
+        nB.x = __shfl_sync(0xffffffffu, tab, 4);
+        nB.y = __shfl_sync(0xffffffffu, tab, 5);
+        nB.z = __shfl_sync(0xffffffffu, tab, 6);
+        nB.w = __shfl_sync(0xffffffffu, tab, 7);
+        if (k + 1 < nt) tab = tab_load(k + 1);
         if (lvl != lvl_prev && lvl_prev >= 0)
         {
             if (sxm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][0] / sxm);
@@ -220,12 +244,9 @@ euler2d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         const size_t pb   = (size_t)p * G::FLAT;
         const bool   bot  = (r0 == 0), top = (r0 + BAND == S);
 
-        // ---- halo tables of the task's patch, hoisted: 4 relation bytes and 8 neighbor indices in
-        // three independent vector loads.  (Looked up per gather they made every ghost a chain of
-        // three dependent global loads -- relation, index, value -- and 20 % of all stall samples.)
-        const uint32_t mb = __ldg(reinterpret_cast<const uint32_t*>(a.meta) + p);
-        const int4     nA = __ldg(reinterpret_cast<const int4*>(a.nbr) + 2 * (size_t)p);
-        const int4     nB = __ldg(reinterpret_cast<const int4*>(a.nbr) + 2 * (size_t)p + 1);
+        // (halo tables mb / nA / nB of the patch: resolved once per task above.  Looked up per
+        // gather they made every ghost a chain of three dependent global loads -- relation, index,
+        // value -- and 20 % of all stall samples.)
 
         // ---- ghost value of padded cell (row, col) across face d, or the stored ghost when the
         // tables say "none" / the caller asked to trust materialised halos.  Same index arithmetic

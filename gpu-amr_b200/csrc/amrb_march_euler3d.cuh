@@ -196,16 +196,45 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     // when tasks differ in cost (coarse/fine faces), which keeps the ghost gathers in L2.
     const int n_tasks = n_items * C::NB;
     const int gw = blockIdx.x * WPC + warp, nw_all = gridDim.x * WPC; // warp of the grid
-    auto next_tau = [&](int prev) -> int {
-        if (a.queue == nullptr) return prev + nw_all;
-        unsigned int t = 0;
-        if (lane == 0) t = atomicAdd(a.queue, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        return (t < 0x40000000u) ? nw_all + (int)t : n_tasks;
+    int          tau_cur = (gw < n_tasks) ? gw : n_tasks; // n_tasks = "none"
+    int          tau_nxt = n_tasks;
+    unsigned int nxt_raw = 0;     // lane 0: value drawn from the counter, not yet broadcast
+    bool         nxt_known = true;
+    int          kc = 0;          // sequence number of the current task
+    // draw the task after tau_cur; the atomic's result is only broadcast when it is first needed
+    // (resolve_next), so its latency hides behind the planes in between
+    auto fetch_next = [&]() {
+        if (a.queue == nullptr)
+        {
+            tau_nxt   = tau_cur + nw_all;
+            nxt_known = true;
+        }
+        else
+        {
+            if (lane == 0) nxt_raw = atomicAdd(a.queue, 1u);
+            nxt_known = false;
+        }
     };
-    int tau_cur = (gw < n_tasks) ? gw : n_tasks; // n_tasks = "none"
-    int tau_nxt = (tau_cur < n_tasks) ? next_tau(tau_cur) : n_tasks;
-    int kc      = 0;                             // sequence number of the current task
+    auto resolve_next = [&]() {
+        if (nxt_known) return;
+        const unsigned int t = __shfl_sync(0xffffffffu, nxt_raw, 0);
+        tau_nxt              = (t < 0x40000000u) ? nw_all + (int)t : n_tasks;
+        nxt_known            = true;
+    };
+    if (tau_cur < n_tasks) fetch_next();
+
+    // halo tables of a task's patch, one 32-bit piece per lane (lanes 0-23: the 6 x 4 neighbor indices,
+    // lane 24: level, lanes 25-30: the 6 relation bytes): loaded for the NEXT task while the current
+    // one is marched and handed round by shuffles, so that no task starts with a table lookup
+    auto tab_load = [&](int tau) -> int {
+        const int item = tau / C::NB;
+        const int q    = a.list ? a.list[item] : item;
+        if (lane < 24) return __ldg(a.nbr + (size_t)q * (G::NDIR * G::KF) + lane);
+        if (lane == 24) return __ldg(a.level + q);
+        if (lane < 31) return (int)__ldg(a.meta + (size_t)q * G::NDIR + (lane - 25));
+        return 0;
+    };
+    int tab = (tau_cur < n_tasks) ? tab_load(tau_cur) : 0, tab_nxt = 0;
 
     auto task_at = [&](int tau, int& p, int& bx, int& by) {
         const int item = tau / C::NB;
@@ -226,6 +255,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     int  ik = 0, ic = 0, ist = 0; // next chunk to issue: task, chunk in task, stage
     auto issue_next = [&]() {
         // the producer is at most NS chunks ahead: inside the current task or the next one
+        if (ik != kc) resolve_next();
         const int tau = (ik == kc) ? tau_cur : tau_nxt;
         if (tau >= n_tasks) return;
         int p, bx, by;
@@ -282,7 +312,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     {
         int p, bx, by;
         task_at(tau_cur, p, bx, by);
-        const int lvl = a.level[p];
+        const int lvl = __shfl_sync(0xffffffffu, tab, 24);
         if (lvl != lvl_prev && lvl_prev >= 0)
         {
             if (sxm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][0] / sxm);
@@ -322,9 +352,13 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         const int ioff = i_y * P + i_x;
         GhostSrc3 gs;
         {
-            // relation byte and the four neighbor indices of the side in two independent loads
-            const int  bm  = a.meta[(size_t)p * G::NDIR + bd];
-            const int4 bnb = __ldg(reinterpret_cast<const int4*>(a.nbr) + (size_t)p * G::NDIR + bd);
+            // relation byte and the four neighbor indices of the side, from the prefetched tables
+            const int bm = __shfl_sync(0xffffffffu, tab, 25 + bd);
+            int4      bnb;
+            bnb.x = __shfl_sync(0xffffffffu, tab, bd * 4);
+            bnb.y = __shfl_sync(0xffffffffu, tab, bd * 4 + 1);
+            bnb.z = __shfl_sync(0xffffffffu, tab, bd * 4 + 2);
+            bnb.w = __shfl_sync(0xffffffffu, tab, bd * 4 + 3);
             const int  rel = (!internal && a.lazy_halo) ? (bm & 3) : 0;
             int f_y = g_y, f_x = g_x; // mirrored into the neighbor's frame (patch_utils.hpp:322-327)
             if (side < 2)
@@ -424,9 +458,13 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         };
         // ghost cells of this lane's column pair across the z faces (d = 0 below, 1 above)
         auto zghost = [&](int d, double (&vA)[NV], double (&vB)[NV]) {
-            const int  m   = a.meta[(size_t)p * G::NDIR + d];
-            const int4 nb  = __ldg(reinterpret_cast<const int4*>(a.nbr) + (size_t)p * G::NDIR + d);
-            const int  rel = a.lazy_halo ? (m & 3) : 0;
+            const int m = __shfl_sync(0xffffffffu, tab, 25 + d);
+            int4      nb;
+            nb.x = __shfl_sync(0xffffffffu, tab, d * 4);
+            nb.y = __shfl_sync(0xffffffffu, tab, d * 4 + 1);
+            nb.z = __shfl_sync(0xffffffffu, tab, d * 4 + 2);
+            nb.w = __shfl_sync(0xffffffffu, tab, d * 4 + 3);
+            const int rel = a.lazy_halo ? (m & 3) : 0;
             const int      y = H + y0 + yy, x = H + x0 + 2 * xq;
             const int      zi = d ? H + S : H - 1, zf = d ? H : H + S - 1; // ghost plane, mirrored
             int            q = p, dB = 1, fin = 0;
@@ -716,6 +754,12 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
 #pragma unroll 1
         for (int z = 0; z < S; ++z)
         {
+            if (z == 2)
+            {
+                // the next task is known by now: request its halo tables
+                resolve_next();
+                if (tau_nxt < n_tasks) tab_nxt = tab_load(tau_nxt);
+            }
             plane_step(z, s0, s1, z > 0, z == S - 1);
             s0 = s1;
         }
@@ -736,8 +780,10 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         }
         __syncwarp(); // sBF is rewritten by the next task
         ++kc;
+        resolve_next();
         tau_cur = tau_nxt;
-        if (tau_cur < n_tasks) tau_nxt = next_tau(tau_cur);
+        tab     = tab_nxt;
+        if (tau_cur < n_tasks) fetch_next();
     }
 
     if (a.sc.dtmin_out != nullptr)

@@ -163,8 +163,7 @@ struct Inst
         {
             // AMRB_VARIANT: 0 = default (plane-marching kernel for 8^3 patches; for 16^3 the
             // block-cooperative pipeline, which is faster there: the per-warp TMA copy rate limits the
-            // marching kernel's 1 152 B row-block copies); 11/12/13 = marching kernel with other ring /
-            // CTA shapes; 10 = block-cooperative pipeline (second generation)
+            // marching kernel's 1 152 B row-block copies); 11/12 = marching kernel with other ring shapes; 10 = block-cooperative pipeline (second generation)
             static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
             const bool march_default = (S == 8);
             if (v != 10 && (v != 0 || march_default))
@@ -173,8 +172,6 @@ struct Inst
                     march3<1, 4, 4, 2>(st, a, n_items);
                 else if (v == 12)
                     march3<1, 3, 4, 3>(st, a, n_items);
-                else if (v == 13)
-                    march3<(S == 8 ? 2 : 1), (S == 8 ? 2 : 4), 5, 2>(st, a, n_items);
                 else
                     march3<(S == 8 ? 2 : 1), (S == 8 ? 2 : 4), 4, 2>(st, a, n_items);
                 return;

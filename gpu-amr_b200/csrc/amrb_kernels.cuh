@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
     double*   sW = sU + NV * TILE;                      // [NW][TILE]  p, a, u_x, u_y(, u_z)
     __shared__ __align__(8) uint64_t bar;
     __shared__ double red[R * (NT / 32)];
+    __shared__ int32_t sNbr[G::NDIR * G::KF]; // halo tables of the patch, fetched while the tile lands
+    __shared__ int     sMeta[G::NDIR];
 
     const int item = blockIdx.x / NBANDS;
     const int band = blockIdx.x % NBANDS;
@@ -348,6 +350,11 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
 #pragma unroll
         for (int f = 0; f < NV; ++f) bulk_g2s(sU + f * TILE, a.cur.p[f] + goff, TILE * 8, &bar);
     }
+
+    // halo tables of the patch: independent loads issued with the copy in flight (looked up per ghost
+    // item they were a chain of three dependent global loads: relation, neighbor index, value)
+    if (tid < G::NDIR * G::KF) sNbr[tid] = a.nbr[(size_t)p * (G::NDIR * G::KF) + tid];
+    if (tid >= 32 && tid < 32 + G::NDIR) sMeta[tid - 32] = a.meta[(size_t)p * G::NDIR + (tid - 32)];
 
     // scalar work overlapped with the copy
     double       rem_after;
@@ -369,6 +376,7 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
     // ghost gather: prefetch sources into registers while the bulk copy is in flight? the gather
     // writes shared memory the copy also writes, so it must be ordered after the wait.
     mbar_wait(&bar, 0);
+    __syncthreads(); // sNbr / sMeta visible
 
     if (a.lazy_halo)
     {
@@ -405,9 +413,9 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
                 }
                 idx[0] = H + t0 + t;
             }
-            const int m = a.meta[(size_t)p * G::NDIR + d];
+            const int m = sMeta[d];
             if ((m & 3) == 0) continue;
-            const int32_t* nb = a.nbr + ((size_t)p * G::NDIR + d) * G::KF;
+            const int32_t* nb = sNbr + d * G::KF;
             int            lo = (idx[0] - row0) * P0;
 #pragma unroll
             for (int k = 1; k < R; ++k) lo += idx[k] * G::pitch(k);

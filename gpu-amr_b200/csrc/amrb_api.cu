@@ -161,12 +161,11 @@ struct Inst
     {
         if constexpr (EQ == kEqEuler && R == 3 && H == 1 && S % 8 == 0)
         {
-            // AMRB_VARIANT: 0 = default (plane-marching kernel for 8^3 patches; for 16^3 the
-            // block-cooperative pipeline, which is faster there: the per-warp TMA copy rate limits the
-            // marching kernel's 1 152 B row-block copies); 11/12 = marching kernel with other ring shapes; 10 = block-cooperative pipeline (second generation)
+            // AMRB_VARIANT: 0 = plane-marching kernel (default; ring of 2-plane TMA copies for 8^3 patches,
+            // of per-lane cp.async row blocks for 16^3); 11/12 = other ring shapes; 10 = block-cooperative
+            // pipeline (second generation)
             static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
-            const bool march_default = (S == 8);
-            if (v != 10 && (v != 0 || march_default))
+            if (v != 10)
             {
                 if (v == 11)
                     march3<1, 4, 4, 2>(st, a, n_items);

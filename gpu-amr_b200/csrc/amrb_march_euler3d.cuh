@@ -44,6 +44,17 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// 16-byte variant and "arrive on an mbarrier once my earlier cp.async have landed" (count not
+// incremented: the barrier is initialised with one arrival per lane)
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
 {
@@ -247,7 +258,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     if (lane == 0)
     {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
+        for (int s = 0; s < NS; ++s) mbar_init(&bar[s], C::WHOLE ? 1 : 32);
     }
     __syncwarp();
 
@@ -260,28 +271,38 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         if (tau >= n_tasks) return;
         int p, bx, by;
         task_at(tau, p, bx, by);
-        if (lane == 0)
+        double* dst = ring + ist * C::STAGE;
+        if constexpr (C::WHOLE)
         {
-            double* dst = ring + ist * C::STAGE;
-            mbar_expect_tx(&bar[ist], C::STAGE * 8);
-            if constexpr (C::WHOLE)
+            // 8^3 patches: CR whole padded planes of a field are contiguous -> one TMA bulk copy each
+            if (lane == 0)
             {
+                mbar_expect_tx(&bar[ist], C::STAGE * 8);
                 const size_t go = (size_t)p * G::FLAT + (size_t)(H + ic * CR) * PP;
 #pragma unroll
                 for (int f = 0; f < NV; ++f)
                     bulk_g2s(dst + f * FS, a.cur.p[f] + go, FS * 8, &bar[ist]);
             }
-            else
-            {
-                const size_t go =
-                    (size_t)p * G::FLAT + (size_t)(H + ic * CR) * PP + (size_t)(H + 8 * by) * P;
+        }
+        else
+        {
+            // wider patches: the block's 8 padded rows of a field-plane are only 8 P doubles; a warp's
+            // bulk copies complete one at a time (tools/tma_bench.cu), so copies this small cannot feed
+            // the march.  All lanes move 16-byte pieces with cp.async instead and arrive on the stage's
+            // mbarrier when their pieces have landed (32 arrivals per phase).
+            const size_t go =
+                (size_t)p * G::FLAT + (size_t)(H + ic * CR) * PP + (size_t)(H + 8 * by) * P;
 #pragma unroll
-                for (int f = 0; f < NV; ++f)
+            for (int f = 0; f < NV; ++f)
 #pragma unroll
-                    for (int j = 0; j < CR; ++j)
-                        bulk_g2s(dst + f * FS + j * PLD, a.cur.p[f] + go + (size_t)j * PP, PLD * 8,
-                                 &bar[ist]);
-            }
+                for (int j = 0; j < CR; ++j)
+                {
+                    const double* src = a.cur.p[f] + go + (size_t)j * PP;
+                    double*       d   = dst + f * FS + j * PLD;
+#pragma unroll
+                    for (int i = lane; i < PLD / 2; i += 32) cp_async16(d + 2 * i, src + 2 * i);
+                }
+            cp_async_mbar_arrive(&bar[ist]);
         }
         if (++ic == C::NCH)
         {

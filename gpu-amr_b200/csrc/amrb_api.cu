@@ -142,11 +142,11 @@ struct Inst
         return best;
     }
     // 3D warp-autonomous plane-marching kernel (amrb_march_euler3d.cuh)
-    template <int CR, int NS, int WPC, int MINB>
+    template <int CR, int NS, int WPC, int MINB, int CPRING = 0>
     static void march3(cudaStream_t st, const StepArgs& a, int n_items)
     {
         using MC = March3Cfg<S, H, CR, NS, WPC>;
-        auto k   = euler3d_march_kernel<S, H, CR, NS, WPC, MINB>;
+        auto k   = euler3d_march_kernel<S, H, CR, NS, WPC, MINB, CPRING>;
         static bool prepared = false;
         if (!prepared)
         {
@@ -162,7 +162,8 @@ struct Inst
         if constexpr (EQ == kEqEuler && R == 3 && H == 1 && S % 8 == 0)
         {
             // AMRB_VARIANT: 0 = plane-marching kernel (default; ring of 2-plane TMA copies for 8^3 patches,
-            // of per-lane cp.async row blocks for 16^3); 11/12 = other ring shapes; 10 = block-cooperative
+            // of per-lane cp.async row blocks for 16^3); 11/12 = other ring shapes; 14/15 = cp.async ring for
+            // 8^3 as well (2-plane / 1-plane chunks); 10 = block-cooperative
             // pipeline (second generation)
             static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
             if (v != 10)
@@ -171,6 +172,10 @@ struct Inst
                     march3<1, 4, 4, 2>(st, a, n_items);
                 else if (v == 12)
                     march3<1, 3, 4, 3>(st, a, n_items);
+                else if (v == 14)
+                    march3<(S == 8 ? 2 : 1), (S == 8 ? 2 : 4), 4, 2, 1>(st, a, n_items);
+                else if (v == 15)
+                    march3<1, 4, 4, 2, 1>(st, a, n_items);
                 else
                     march3<(S == 8 ? 2 : 1), (S == 8 ? 2 : 4), 4, 2>(st, a, n_items);
                 return;

@@ -177,7 +177,7 @@ struct March3Cfg
     static_assert((PLD * 8) % 16 == 0 && (WARP_DOUBLES * 8) % 16 == 0, "bulk copy alignment");
 };
 
-template <int S, int H, int CR, int NS, int WPC, int MINB>
+template <int S, int H, int CR, int NS, int WPC, int MINB, int CPRING = 0>
 __global__ void __launch_bounds__(WPC * 32, MINB)
 euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
 {
@@ -258,7 +258,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     if (lane == 0)
     {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&bar[s], C::WHOLE ? 1 : 32);
+        for (int s = 0; s < NS; ++s) mbar_init(&bar[s], (C::WHOLE && !CPRING) ? 1 : 32);
     }
     __syncwarp();
 
@@ -272,7 +272,21 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         int p, bx, by;
         task_at(tau, p, bx, by);
         double* dst = ring + ist * C::STAGE;
-        if constexpr (C::WHOLE)
+        if constexpr (C::WHOLE && CPRING)
+        {
+            // (experiment) the same contiguous planes moved as 16-byte cp.async pieces by all lanes
+            const size_t go = (size_t)p * G::FLAT + (size_t)(H + ic * CR) * PP;
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                const double* src = a.cur.p[f] + go;
+                double*       d   = dst + f * FS;
+#pragma unroll
+                for (int i = lane; i < FS / 2; i += 32) cp_async16(d + 2 * i, src + 2 * i);
+            }
+            cp_async_mbar_arrive(&bar[ist]);
+        }
+        else if constexpr (C::WHOLE)
         {
             // 8^3 patches: CR whole padded planes of a field are contiguous -> one TMA bulk copy each
             if (lane == 0)

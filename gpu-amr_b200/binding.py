@@ -82,6 +82,8 @@ def lib():
                                       C.POINTER(vp), vp, C.POINTER(vp)],
         "amrb_pool_destroy": [vp],
         "amrb_pool_set_topology": [vp, sz, sz, i32p, i8p, i32p, i8p],
+        "amrb_pool_set_topology_from_ids": [vp, C.POINTER(C.c_uint64), sz],
+        "amrb_pool_get_tables": [vp, i32p, C.POINTER(C.c_uint8), i32p],
         "amrb_pool_set_physics": [vp, C.POINTER(C.c_double), C.c_double, C.c_double],
         "amrb_pool_upload": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_download": [vp, C.c_int, sz, sz, dp],
@@ -255,6 +257,19 @@ class DevicePool:
         check(self.L.amrb_pool_set_topology(self.h, n, n if n_total is None else n_total,
                                             _ptr(levels), _ptr(rel), _ptr(nbr), _ptr(quad)))
 
+    def set_topology_from_ids(self, ids):
+        """tables built on the device from the ascending leaf ids (single GPU, no ghost slots)"""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        check(self.L.amrb_pool_set_topology_from_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint64)), len(ids)))
+
+    def get_tables(self, n, rank):
+        """device tables in the compact device form: levels[n], meta[n][2R], nbr[n][2R][2^(R-1)]"""
+        levels = np.zeros(n, np.int32)
+        meta = np.zeros((n, 2 * rank), np.uint8)
+        nbr = np.zeros((n, 2 * rank, 1 << (rank - 1)), np.int32)
+        check(self.L.amrb_pool_get_tables(self.h, _ptr(levels), meta.ctypes.data_as(C.POINTER(C.c_uint8)), _ptr(nbr)))
+        return levels, meta, nbr
+
     def upload(self, field, data, first=0):
         data = np.ascontiguousarray(data, np.float64).reshape(-1, self.flat)
         check(self.L.amrb_pool_upload(self.h, field, first, data.shape[0], _ptr(data)))
@@ -328,8 +343,12 @@ class DeviceTree:
         self._push_topology()
 
     def _push_topology(self):
-        levels, rel, nbr, quad = self.tree.tables()
-        self.pool.set_topology(levels, rel, nbr, quad)
+        # tables are built on the device from the leaf ids (AMRB_DEVICE_TOPOLOGY=0: host build + upload)
+        if os.environ.get("AMRB_DEVICE_TOPOLOGY", "1") != "0":
+            self.pool.set_topology_from_ids(self.tree.ids())
+        else:
+            levels, rel, nbr, quad = self.tree.tables()
+            self.pool.set_topology(levels, rel, nbr, quad)
 
     @property
     def size(self):

@@ -308,6 +308,8 @@ struct amrb_pool
     // batch scalars
     unsigned long long* d_dtmin = nullptr;
     unsigned int*       d_queue = nullptr; // dynamic task counter of the 3D marching kernel
+    uint64_t*           d_ids = nullptr;   // leaf ids (device-side table build)
+    size_t              ids_cap = 0;
     double*      d_remaining = nullptr;
     double*      d_dts       = nullptr;
     double*      h_dts       = nullptr; // pinned
@@ -662,6 +664,7 @@ amrb_status amrb_pool_destroy(amrb_pool* p)
     cudaFree(p->d_level);
     cudaFree(p->d_dtmin);
     if (p->d_queue) cudaFree(p->d_queue);
+    if (p->d_ids) cudaFree(p->d_ids);
     cudaFree(p->d_remaining);
     cudaFree(p->d_dts);
     cudaFree(p->d_stage);
@@ -760,6 +763,75 @@ amrb_status amrb_pool_set_topology(amrb_pool* p, size_t n_owned, size_t n_total,
     p->n_owned     = n_owned;
     p->n_total     = n_total;
     p->carry_valid = false;
+    return AMRB_OK;
+}
+
+
+// Tables of the whole leaf set built ON THE DEVICE from the ascending leaf ids: one
+// H2D copy of 8 bytes per leaf instead of the host table build and 10 / 28 bytes per
+// patch-direction.  Single-GPU form: no ghost slots (n_total == n_owned == n).
+amrb_status amrb_pool_set_topology_from_ids(amrb_pool* p, const uint64_t* ids, size_t n)
+{
+    if (!p || !ids) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (n == 0) return fail(AMRB_ERR_ARGUMENT, "bad patch counts");
+    if (n > p->capacity) return fail(AMRB_ERR_CAPACITY, "patch count exceeds pool capacity");
+    for (size_t i = 0; i < n; ++i)
+    {
+        if ((int)(ids[i] & 63u) > p->lay.depth) return fail(AMRB_ERR_ARGUMENT, "level out of range");
+        if (i && !(ids[i - 1] < ids[i])) return fail(AMRB_ERR_ARGUMENT, "leaf ids must be strictly ascending");
+    }
+    AMRB_TRY(set_device(p));
+    const int R = p->lay.rank, ND = 2 * R, KF = 1 << (R - 1);
+    if (p->table_cap < n)
+    {
+        cudaFree(p->d_nbr);
+        cudaFree(p->d_meta);
+        cudaFree(p->d_level);
+        p->d_nbr = nullptr;
+        p->d_meta = nullptr;
+        p->d_level = nullptr;
+        p->table_cap = 0;
+        const size_t cap = std::max(n, std::min(p->capacity, n * 2));
+        AMRB_CUDA(cudaMalloc(&p->d_nbr, cap * ND * KF * sizeof(int32_t)));
+        AMRB_CUDA(cudaMalloc(&p->d_meta, cap * ND));
+        AMRB_CUDA(cudaMalloc(&p->d_level, cap * sizeof(int32_t)));
+        p->table_cap = cap;
+    }
+    if (p->ids_cap < n)
+    {
+        cudaFree(p->d_ids);
+        p->d_ids   = nullptr;
+        p->ids_cap = 0;
+        const size_t cap = std::max(n, std::min(p->capacity, n * 2));
+        AMRB_CUDA(cudaMalloc(&p->d_ids, cap * sizeof(uint64_t)));
+        p->ids_cap = cap;
+    }
+    // the previous tables may still be in use by launches in flight
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    AMRB_CUDA(cudaMemcpyAsync(p->d_ids, ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
+    const long threads = (long)n * ND;
+    topology_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, p->stream>>>(
+        p->d_ids, (int)n, R, p->lay.depth, p->d_level, p->d_meta, p->d_nbr);
+    AMRB_TRY(check_launch(p, "topology_kernel"));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream)); // `ids` may be released by the caller
+    p->n_owned     = n;
+    p->n_total     = n;
+    p->carry_valid = false;
+    return AMRB_OK;
+}
+
+// device tables back to the host in the compact device form (tests, debugging):
+// levels[n], meta[n][2R] = relation | quadrant bits << 2, nbr[n][2R][2^(R-1)]
+amrb_status amrb_pool_get_tables(amrb_pool* p, int32_t* levels, uint8_t* meta, int32_t* nbr)
+{
+    if (!p || !levels || !meta || !nbr) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    const int R = p->lay.rank, ND = 2 * R, KF = 1 << (R - 1);
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    AMRB_CUDA(cudaMemcpy(levels, p->d_level, p->n_owned * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    AMRB_CUDA(cudaMemcpy(meta, p->d_meta, p->n_owned * ND, cudaMemcpyDeviceToHost));
+    AMRB_CUDA(cudaMemcpy(nbr, p->d_nbr, p->n_owned * ND * KF * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return AMRB_OK;
 }
 

@@ -213,6 +213,115 @@ halo_kernel(FieldPtrs cur, const int32_t* __restrict__ nbr, const uint8_t* __res
     }
 }
 
+
+// ---- neighbor / halo tables on the device ------------------------------------------
+// One thread per (leaf, direction): the relation, neighbor indices and contact quadrant are derived
+// from the ASCENDING array of leaf ids by key lookup (binary search), the same set-based rule as the
+// host builder (amrb_topology.cpp: amrb_tree::neighbor; reference: ndtree/neighbor.hpp:291-572,
+// ndtree.hpp:1606-1660).  id = morton(x, y[, z]) << 6 | level, x in bit 0 of every interleaved group.
+__device__ __forceinline__ uint64_t topo_encode(int rank, const uint32_t (&c)[3], int level, int depth)
+{
+    uint64_t m = 0;
+    for (int b = 0; b <= depth; ++b)
+        for (int a = 0; a < rank; ++a) m |= (uint64_t)((c[a] >> b) & 1u) << (rank * b + a);
+    return (m << 6) | (uint64_t)level;
+}
+__device__ __forceinline__ int topo_find(const uint64_t* __restrict__ ids, int n, uint64_t key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (ids[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (lo < n && ids[lo] == key) ? lo : -1;
+}
+__global__ void __launch_bounds__(256)
+topology_kernel(const uint64_t* __restrict__ ids, int n, int rank, int depth, int32_t* __restrict__ level,
+                uint8_t* __restrict__ meta, int32_t* __restrict__ nbr)
+{
+    const int ND = 2 * rank, KF = 1 << (rank - 1);
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n * ND) return;
+    const int      i = (int)(t / ND), d = (int)(t % ND);
+    const uint64_t id  = ids[i];
+    const int      lvl = (int)(id & 63u);
+    if (d == 0) level[i] = lvl;
+    uint32_t c[3] = { 0u, 0u, 0u };
+    {
+        const uint64_t m = id >> 6;
+        for (int b = 0; b <= depth; ++b)
+            for (int a = 0; a < rank; ++a) c[a] |= (uint32_t)((m >> (rank * b + a)) & 1ull) << b;
+    }
+    const int      dim = d >> 1, pos = d & 1;
+    const int      ax  = rank - 1 - dim; // layout dim k <-> morton axis rank-1-k
+    const uint32_t span = 1u << depth, e = 1u << (depth - lvl);
+    uint32_t       nn[3] = { c[0], c[1], c[2] };
+    nn[ax] = (pos ? c[ax] + e : c[ax] + span - e) & (span - 1); // periodic domain
+    int32_t out[4] = { -1, -1, -1, -1 };
+    int     m      = 0; // relation | quadrant bits << 2
+    int     li     = topo_find(ids, n, topo_encode(rank, nn, lvl, depth));
+    if (li >= 0)
+    {
+        m      = 1; // same
+        out[0] = li;
+    }
+    else
+    {
+        bool done = false;
+        if (lvl > 0)
+        {
+            const uint32_t E = e << 1;
+            uint32_t       cn[3];
+            for (int a = 0; a < 3; ++a) cn[a] = nn[a] & ~(E - 1);
+            li = topo_find(ids, n, topo_encode(rank, cn, lvl - 1, depth));
+            if (li >= 0)
+            {
+                m      = 3; // coarser; contact quadrant: normal 0 for a positive direction, 1 for negative
+                out[0] = li;
+                for (int k = 0; k < rank; ++k)
+                {
+                    const int q = (k == dim) ? (pos ? 0 : 1) : (int)((c[rank - 1 - k] / e) & 1u);
+                    m |= q << (2 + k);
+                }
+                done = true;
+            }
+        }
+        if (!done && lvl < depth)
+        {
+            const uint32_t hh = e >> 1;
+            bool           ok = true;
+            for (int j = 0; j < KF && ok; ++j)
+            {
+                // finer-neighbor order: non-normal layout dims ascending, lowest = bit 0
+                uint32_t cc[3] = { nn[0], nn[1], nn[2] };
+                cc[ax] += pos ? 0u : hh;
+                int bit = 0;
+                for (int k = 0; k < rank; ++k)
+                {
+                    if (k == dim) continue;
+                    if ((j >> bit) & 1) cc[rank - 1 - k] += hh;
+                    ++bit;
+                }
+                li = topo_find(ids, n, topo_encode(rank, cc, lvl + 1, depth));
+                if (li < 0)
+                    ok = false;
+                else
+                    out[j] = li;
+            }
+            if (ok)
+                m = 2; // finer
+            else
+                for (int j = 0; j < 4; ++j) out[j] = -1;
+        }
+    }
+    meta[(size_t)i * ND + d] = (uint8_t)m;
+    for (int k = 0; k < KF; ++k) nbr[((size_t)i * ND + d) * KF + k] = out[k];
+}
+
 // ---- batch scalars (device-resident dt bookkeeping) -----------------------------------------------
 struct StepScalars
 {

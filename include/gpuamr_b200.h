@@ -121,6 +121,14 @@ double*     amrb_pool_next_field(const amrb_pool* pool, int field);
 amrb_status amrb_pool_set_topology(amrb_pool* pool, size_t n_owned, size_t n_total,
                                    const int32_t* levels, const int8_t* rel, const int32_t* nbr,
                                    const int8_t* quad);
+/* the same tables built ON THE DEVICE from the ascending leaf ids (id = morton << 6 | level) of the whole
+ * mesh — replaces the host loop of ndtree::rebuild_halo_exchange_metadata (ndtree.hpp:1606-1660) and its
+ * H2D copy of the metadata by one copy of 8 bytes per leaf and one kernel.  Single-GPU
+ * form (no ghost slots).  Bit-identical to amrb_tree_tables + amrb_pool_set_topology. */
+amrb_status amrb_pool_set_topology_from_ids(amrb_pool* pool, const uint64_t* ids, size_t n);
+/* device tables read back in the compact device form: levels[n], meta[n][2R] = relation | contact-quadrant
+ * bits << 2, nbr[n][2R][2^(R-1)] (tests, debugging) */
+amrb_status amrb_pool_get_tables(amrb_pool* pool, int32_t* levels, uint8_t* meta, int32_t* nbr);
 /* physical domain lengths per *physical* axis (x,y,z) and solver constants
  * (solver/physics_system.hpp:58-85, amr_solver.hpp:62-69) */
 amrb_status amrb_pool_set_physics(amrb_pool* pool, const double* lengths, double gamma,

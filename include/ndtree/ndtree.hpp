@@ -274,12 +274,10 @@ private:
         m_ids.resize(n);
         for (size_type i = 0; i != n; ++i) m_ids[i] = patch_index_t{ raw[i] };
         m_status.assign(n, 0);
-        constexpr size_type       nd = 2 * s_rank, kf = size_type{ 1 } << (s_rank - 1);
-        std::vector<std::int32_t> levels(n), nbr(n * nd * kf);
-        std::vector<std::int8_t>  rel(n * nd), quad(n * nd * s_rank);
-        check(amrb_tree_tables(m_topo, levels.data(), rel.data(), nbr.data(), quad.data()), "amrb_tree_tables");
-        check(amrb_pool_set_topology(m_pool, n, n, levels.data(), rel.data(), nbr.data(), quad.data()),
-              "amrb_pool_set_topology");
+        // neighbor / halo tables: built on the device from the ascending leaf ids (one 8-byte-per-leaf
+        // copy + one kernel) instead of the reference's host loop + metadata upload
+        // (ndtree.hpp:1606-1700)
+        check(amrb_pool_set_topology_from_ids(m_pool, raw, n), "amrb_pool_set_topology_from_ids");
     }
 
     size_type                  m_capacity;

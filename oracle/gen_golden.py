@@ -158,6 +158,24 @@ D t0
 S 3
 D t3
 """, {}),
+    # 8^3 patches on three levels with a regrid (refine + coarsen) between two runs of steps:
+    # coarse/fine faces in all directions for the 3D plane-marching kernel and the 3D plan kernel
+    ("c3_amr", "r3_s8_h1_d5_euler", """
+A
+X
+H 41 400 0 1 2
+X
+I
+X
+D t0
+S 4
+D t4
+H 42 300 300 1 3
+X
+D regrid
+S 3
+D t7
+""", {"t4": "stats", "regrid": "stats", "t7": "stats"}),
     # 3D advection, halo 2
     ("adv3d_h2", "r3_s4_h2_d5_adv", """
 A
@@ -192,7 +210,10 @@ D t5
 def main():
     os.makedirs(GOLD, exist_ok=True)
     total = 0
+    only = set(sys.argv[1:])                 # optional: regenerate only the named fixtures
     for name, cfg, script, opts in CASES:
+        if only and name not in only:
+            continue
         exe = os.path.join(HERE, "_ref", "ref_dump_" + cfg)
         with tempfile.TemporaryDirectory() as td:
             sp, op = os.path.join(td, "s.txt"), os.path.join(td, "o.bin")

@@ -50,8 +50,12 @@ def test_device_matches_reference_dump(amrb, name, mode):
             else:
                 assert rel_err(mine, ref) <= TOL, (name, tag, rel_err(mine, ref))
         else:
+            # stats-only tag: the first patch in full, normalised by the GLOBAL field maximum (a patch
+            # in a quiescent corner holds momenta that are rounding noise of O(1) pressures)
             full = out[tag + "/data"]
-            assert rel_err(full[:, 0, :][..., mask][:, None], g[tag + "/first_patch"][..., mask][:, None]) <= TOL
+            a, b = full[:, 0, :][..., mask], g[tag + "/first_patch"][..., mask]
+            den = np.maximum(np.abs(g[tag + "/max"]), np.abs(b).max(axis=-1))
+            assert (np.abs(a - b).max(axis=-1) / den).max() <= TOL, (name, tag)
             np.testing.assert_allclose(full[..., mask].sum(axis=(1, 2)), g[tag + "/sum"], rtol=1e-12, atol=1e-8)
             np.testing.assert_allclose(full[..., mask].max(axis=(1, 2)), g[tag + "/max"], rtol=TOL)
 

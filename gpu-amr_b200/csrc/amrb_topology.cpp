@@ -86,7 +86,28 @@ struct amrb_tree
 {
     int                   rank = 2, depth = 1;
     std::vector<uint64_t> ids;
-    IdMap                 map;
+    // id -> linear index.  The hash map costs a full pass over the leaves to build (0.1 s at 2e6
+    // leaves), so it is only built when a call is going to do many lookups (table build, a pass
+    // that splits a large share of the leaves); otherwise a lookup is a binary search in the
+    // ascending id array.
+    mutable IdMap         map;
+    mutable bool          map_valid = false;
+
+    void invalidate_map() { map_valid = false; }
+    void ensure_map() const
+    {
+        if (!map_valid)
+        {
+            map.build(ids);
+            map_valid = true;
+        }
+    }
+    int32_t find(uint64_t id) const
+    {
+        if (map_valid) return map.find(id);
+        const auto it = std::lower_bound(ids.begin(), ids.end(), id);
+        return (it != ids.end() && *it == id) ? (int32_t)(it - ids.begin()) : -1;
+    }
     std::vector<int8_t>   plan_kind, plan_child;
     std::vector<int32_t>  plan_src;
 
@@ -110,7 +131,7 @@ struct amrb_tree
         uint32_t       n[3] = { c[0], c[1], c[2] };
         n[ax] = (pos ? c[ax] + e : c[ax] + span() - e) & (span() - 1); // periodic (ndtree.hpp:412-421)
 
-        int32_t li = map.find(encode(n, lvl));
+        int32_t li = find(encode(n, lvl));
         if (li >= 0)
         {
             out.rel    = AMRB_REL_SAME;
@@ -122,7 +143,7 @@ struct amrb_tree
             const uint32_t E = e << 1;
             uint32_t       cn[3];
             for (int a = 0; a < 3; ++a) cn[a] = n[a] & ~(E - 1);
-            li = map.find(encode(cn, lvl - 1));
+            li = find(encode(cn, lvl - 1));
             if (li >= 0)
             {
                 out.rel    = AMRB_REL_COARSER;
@@ -154,7 +175,7 @@ struct amrb_tree
                     if ((j >> bit) & 1) cc[rank - 1 - k] += hh;
                     ++bit;
                 }
-                li = map.find(encode(cc, lvl + 1));
+                li = find(encode(cc, lvl + 1));
                 if (li < 0)
                     ok = false;
                 else
@@ -199,7 +220,7 @@ amrb_status amrb_tree_create(int rank, int depth, amrb_tree** out)
     t->rank      = rank;
     t->depth     = depth;
     t->ids.assign(1, 0ull); // the periodic root (ndtree.hpp:411-421)
-    t->map.build(t->ids);
+    t->invalidate_map();
     *out = t;
     return AMRB_OK;
 }
@@ -219,6 +240,7 @@ amrb_status amrb_tree_tables(const amrb_tree* t, int32_t* levels, int8_t* rel, i
     if (!t || !levels || !rel || !nbr || !quad) return tfail(AMRB_ERR_ARGUMENT, "null argument");
     const int    R = t->rank, ND = 2 * R, KF = 1 << (R - 1);
     const size_t n = t->ids.size();
+    t->ensure_map(); // 2R lookups per leaf
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)n; ++i)
     {
@@ -276,6 +298,8 @@ amrb_status amrb_tree_reconstruct(amrb_tree* t, const int8_t* flags, size_t capa
         if (ok) coarsen_first.push_back((int32_t)i);
     }
     if (work.empty() && coarsen_first.empty()) return AMRB_OK;
+    // ripple + veto look up 2R neighbors per splitting leaf / per child of a merging family
+    if ((work.size() + coarsen_first.size() * FAN) * (size_t)ND > n / 4) t->ensure_map();
 
     // ---- 2:1 ripple: a coarser neighbor of a splitting leaf splits too (ndtree.hpp:1127-1166)
     for (size_t w = 0; w < work.size(); ++w)
@@ -366,7 +390,7 @@ amrb_status amrb_tree_reconstruct(amrb_tree* t, const int8_t* flags, size_t capa
     if (capacity && ids.size() > capacity)
         return tfail(AMRB_ERR_CAPACITY, "reconstruct would exceed the patch capacity");
     t->ids.swap(ids);
-    t->map.build(t->ids);
+    t->invalidate_map();
     t->plan_kind.swap(kind);
     t->plan_src.swap(src);
     t->plan_child.swap(child);

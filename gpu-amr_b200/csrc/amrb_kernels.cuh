@@ -492,7 +492,10 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
         // inner ghost layer only: the stencil never reads beyond one cell (amr_solver.hpp:317-321)
         constexpr int SIDE  = (R == 2) ? BAND : BAND * S; // ghost cells per non-slowest face in band
         constexpr int ITEMS = 2 * G::FACE + (G::NDIR - 2) * SIDE;
-        for (int it = tid; it < ITEMS; it += NT)
+        // 3D advection has no motion along z (velocity {1, 0.5, 0}, AdvectionPhysics.hpp:24): its z-face
+        // fluxes are exactly zero, so neither the z ghosts nor the z fluxes are evaluated
+        constexpr int FIRST = (EQ == kEqAdvection && R == 3) ? 2 * G::FACE : 0;
+        for (int it = FIRST + tid; it < ITEMS; it += NT)
         {
             int d, idx[R];
             if (it < 2 * G::FACE)
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
         if constexpr (EQ == kEqAdvection)
         {
 #pragma unroll
-            for (int ds = 0; ds < R; ++ds)
+            for (int ds = 0; ds < ((R == 3) ? 2 : R); ++ds) // ds = 2: zero velocity, zero flux
             {
                 const int    st = G::pitch(R - 1 - ds);
                 const double v  = adv_vel(ds);

@@ -454,10 +454,23 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
     __syncthreads();
     if (tid == 0)
     {
-        mbar_expect_tx(&bar, NV * TILE * 8);
-        const size_t goff = (size_t)p * G::FLAT + (size_t)row0 * P0;
+        if constexpr (EQ == kEqAdvection && R == 3)
+        {
+            // no z coupling (see the gather below): the ghost planes below / above the band are not
+            // staged at all
+            mbar_expect_tx(&bar, NV * BAND * P0 * 8);
+            const size_t goff = (size_t)p * G::FLAT + (size_t)(row0 + 1) * P0;
 #pragma unroll
-        for (int f = 0; f < NV; ++f) bulk_g2s(sU + f * TILE, a.cur.p[f] + goff, TILE * 8, &bar);
+            for (int f = 0; f < NV; ++f)
+                bulk_g2s(sU + f * TILE + P0, a.cur.p[f] + goff, BAND * P0 * 8, &bar);
+        }
+        else
+        {
+            mbar_expect_tx(&bar, NV * TILE * 8);
+            const size_t goff = (size_t)p * G::FLAT + (size_t)row0 * P0;
+#pragma unroll
+            for (int f = 0; f < NV; ++f) bulk_g2s(sU + f * TILE, a.cur.p[f] + goff, TILE * 8, &bar);
+        }
     }
 
     // halo tables of the patch: independent loads issued with the copy in flight (looked up per ghost

@@ -316,6 +316,8 @@ struct amrb_pool
     size_t       scal_cap = 0, batch_steps = 0, batch_k = 0;
     bool         batch_open = false, batch_pending = false, carry_valid = false;
     bool         pending_in_graph = false; // the batch was enqueued under stream capture: no event
+    bool         lazy_halos = false;       // materialise face halos only when something observes them
+    bool         halos_stale = false;
     bool         step_touched = false;
     cudaEvent_t  batch_done = nullptr;
     // staging
@@ -858,6 +860,7 @@ amrb_status amrb_pool_download(amrb_pool* p, int field, size_t first, size_t n, 
 {
     AMRB_TRY(check_range(p, field, first, n, host));
     AMRB_TRY(set_device(p));
+    AMRB_TRY(amrb_pool_ensure_halos(p));
     AMRB_CUDA(cudaMemcpyAsync(host, p->cur.p[field] + first * p->flat, n * p->flat * sizeof(double),
                               cudaMemcpyDeviceToHost, p->stream));
     AMRB_CUDA(cudaStreamSynchronize(p->stream));
@@ -900,7 +903,27 @@ amrb_status amrb_pool_halo_exchange(amrb_pool* p)
     AMRB_TRY(need_topology(p));
     AMRB_TRY(set_device(p));
     p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
+    p->halos_stale = false;
     return check_launch(p, "halo_kernel");
+}
+
+// Lazy materialisation of the face halos (drop-in headers): the fused step never reads stored ghosts, so
+// the post-condition of a reference step "face halos of the current buffer are filled"
+// (amr_solver.hpp:351-352) only has to hold when something OBSERVES the padded patches: a download, the
+// refinement criterion, a raw device pointer handed out, the refine / coarsen data motion.  A driver
+// that advances one step per call (the reference's benchmarks) otherwise pays one halo launch per step
+// (19 % of the GPU time of bench_fvm_solver_integration_active_amr, profiles/r01v_*).
+amrb_status amrb_pool_set_lazy_halos(amrb_pool* p, int on)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    p->lazy_halos = on != 0;
+    return AMRB_OK;
+}
+amrb_status amrb_pool_ensure_halos(amrb_pool* p)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (!p->halos_stale || !p->d_nbr || p->n_owned == 0) return AMRB_OK;
+    return amrb_pool_halo_exchange(p);
 }
 
 // ------------------------------------------------------------------------------ stepping
@@ -1072,6 +1095,11 @@ amrb_status amrb_pool_advance_batch_async(amrb_pool* p, size_t steps, double rem
         AMRB_TRY(amrb_pool_step_partial(p, nullptr, 0));
         AMRB_TRY(amrb_pool_step_commit(p));
     }
+    if (p->lazy_halos && p->mode != 1)
+    {
+        p->halos_stale = true;
+        return amrb_pool_batch_end(p, 0);
+    }
     return amrb_pool_batch_end(p, 1);
 }
 
@@ -1138,6 +1166,7 @@ amrb_status amrb_pool_apply_plan(amrb_pool* p, size_t new_size, const int8_t* ki
     if (new_size == 0 || new_size > p->capacity) return fail(AMRB_ERR_CAPACITY, "new size exceeds capacity");
     if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is open");
     AMRB_TRY(set_device(p));
+    AMRB_TRY(amrb_pool_ensure_halos(p)); // copied patches carry their halos along
     const size_t bytes = new_size * (sizeof(int8_t) * 2 + sizeof(int32_t));
     if (p->plan_cap < bytes)
     {
@@ -1170,6 +1199,7 @@ amrb_status amrb_pool_patch_max_flags(amrb_pool* p, int field, double refine_thr
     if (field < 0 || field >= p->lay.nvar) return fail(AMRB_ERR_ARGUMENT, "field out of range");
     AMRB_TRY(need_topology(p));
     AMRB_TRY(set_device(p));
+    AMRB_TRY(amrb_pool_ensure_halos(p)); // the criterion looks at the padded patch
     if (p->flags_cap < p->n_owned)
     {
         cudaFree(p->d_flags);

@@ -153,6 +153,12 @@ amrb_status amrb_pool_download_interior(amrb_pool* pool, int field, size_t first
  *    One launch materialises the face halos of ALL fields of the current buffer, in place.
  * ---------------------------------------------------------------------------------------- */
 amrb_status amrb_pool_halo_exchange(amrb_pool* pool);
+/* lazy materialisation of the face halos: with `on`, amrb_pool_advance_batch_async no longer ends with a
+ * halo fill (post-condition of amr_solver::time_step, amr_solver.hpp:351-352); the fill happens when the
+ * padded patches are observed (amrb_pool_download, amrb_pool_patch_max_flags, amrb_pool_apply_plan) or
+ * on request (amrb_pool_ensure_halos — call it before handing out amrb_pool_field pointers). */
+amrb_status amrb_pool_set_lazy_halos(amrb_pool* pool, int on);
+amrb_status amrb_pool_ensure_halos(amrb_pool* pool);
 
 /* ------------------------------------------------------------------------------------------
  * 5. time stepping — replaces launch_compute_dt_kernel_device, launch_finalize_step_dt,

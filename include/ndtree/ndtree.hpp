@@ -91,6 +91,8 @@ public:
         m_layout.depth    = static_cast<std::int32_t>(patch_index_t::max_depth());
         check(amrb_tree_create(static_cast<int>(s_rank), m_layout.depth, &m_topo), "amrb_tree_create");
         check(amrb_pool_create(&m_layout, capacity, device, &m_pool), "amrb_pool_create");
+        // face halos are materialised when the padded patches are observed, not after every step
+        check(amrb_pool_set_lazy_halos(m_pool, 1), "amrb_pool_set_lazy_halos");
         void* host = nullptr;
         check(amrb_host_pinned_malloc(&host, capacity * s_flat * s_nvar * sizeof(double)), "host mirror");
         m_host = static_cast<double*>(host);
@@ -164,6 +166,7 @@ public:
     [[nodiscard]] auto get_device_buffer() -> patch_t<Map>*
     {
         make_device_current();
+        check(amrb_pool_ensure_halos(m_pool), "get_device_buffer"); // the pointee is a padded patch array
         // the raw pointer is handed to code running on other streams (the reference works on the
         // legacy default stream): order it after everything queued on the pool's stream
         check(amrb_stream_synchronize(amrb_pool_stream(m_pool)), "get_device_buffer");

@@ -162,7 +162,7 @@ struct Inst
         if constexpr (EQ == kEqEuler && R == 3 && H == 1 && S % 8 == 0)
         {
             // AMRB_VARIANT: 0 = plane-marching kernel (default; ring of 2-plane TMA copies for 8^3 patches,
-            // of per-lane cp.async row blocks for 16^3); 11/12 = other ring shapes; 14/15 = cp.async ring for
+            // of per-lane cp.async row blocks for 16^3); 11 = 1-plane chunks, 4 stages; 14/15 = cp.async ring for
             // 8^3 as well (2-plane / 1-plane chunks); 10 = block-cooperative
             // pipeline (second generation)
             static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
@@ -170,8 +170,6 @@ struct Inst
             {
                 if (v == 11)
                     march3<1, 4, 4, 2>(st, a, n_items);
-                else if (v == 12)
-                    march3<1, 3, 4, 3>(st, a, n_items);
                 else if (v == 14)
                     march3<(S == 8 ? 2 : 1), (S == 8 ? 2 : 4), 4, 2, 1>(st, a, n_items);
                 else if (v == 15)

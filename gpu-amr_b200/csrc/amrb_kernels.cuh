@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
     using G               = Geo<R, S, H>;
     using E               = EqTraits<EQ, R>;
     constexpr int NV      = E::NV;
-    constexpr int NW      = E::NW;
+    [[maybe_unused]] constexpr int NW = E::NW;
     constexpr int P0      = G::pitch(0);      // doubles per slowest-dim row
     constexpr int ROWS    = BAND + 2;
     constexpr int TILE    = ROWS * P0;        // doubles per field tile

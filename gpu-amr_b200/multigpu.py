@@ -103,7 +103,8 @@ class ShardedSolver:
         # the next step's slab exchange instead of sitting between two steps
         self.ar_stream = torch.cuda.Stream(device=device)
         self.ar_group = None
-        if world > 1 and dist.get_backend() == "nccl" and os.environ.get("AMRB_AR_GROUP", "1") != "0":
+        if (world > 1 and dist is not None and dist.is_initialized() and dist.get_backend() == "nccl"
+                and os.environ.get("AMRB_AR_GROUP", "1") != "0"):
             self.ar_group = dist.new_group(ranks=list(range(world)))
         self.graphs = {}
         self._dtmin_cache = {}
@@ -240,6 +241,88 @@ class ShardedSolver:
 
     def finish_advance_batch(self, max_steps=0):
         return self.pool.finish_advance_batch(max_steps)
+
+
+# ------------------------------------------------------------------------------- in-process cluster
+class LocalCluster:
+    """All W shards of one mesh inside ONE process on ONE GPU, driven phase by phase: the same
+    ShardPlan, ghost slots, pack / unpack kernels, interior / boundary launches and per-step CFL
+    minimum as the NCCL path, with the slab exchange and the all-reduce done by device-to-device
+    copies.  Test vehicle for the sharding logic on a single-GPU box (the NCCL transport itself is
+    covered by tests/test_multigpu_gpu.py on >= 2 GPUs)."""
+
+    def __init__(self, cfg, host_tree, world, device, torch):
+        self.torch, self.world, self.cfg = torch, world, cfg
+        self.sols = [ShardedSolver(cfg, host_tree, r, world, device, None, torch) for r in range(world)]
+        # where rank r's send segment for rank q starts / where q expects r's data
+        self.send_off = [np.concatenate([[0], np.cumsum(s.in_splits)]).astype(int) for s in self.sols]
+        self.recv_off = [np.concatenate([[0], np.cumsum(s.out_splits)]).astype(int) for s in self.sols]
+        for r, s in enumerate(self.sols):
+            for q, t in enumerate(self.sols):
+                assert s.in_splits[q] == t.out_splits[r], "send / receive plans disagree"
+
+    def _sync(self):
+        self.torch.cuda.synchronize()
+
+    def exchange(self):
+        for s in self.sols:
+            s._pack()
+        self._sync()
+        for r, s in enumerate(self.sols):
+            for q, t in enumerate(self.sols):
+                n = s.in_splits[q]
+                if n:
+                    t.recv_buf[self.recv_off[q][r]:self.recv_off[q][r] + n].copy_(
+                        s.send_buf[self.send_off[r][q]:self.send_off[r][q] + n])
+        self._sync()
+        for s in self.sols:
+            s._unpack()
+        self._sync()
+
+    def halo_exchange(self):
+        self.exchange()
+        for s in self.sols:
+            s.pool.halo_exchange()
+        self._sync()
+
+    def _reduce_dtmin(self, k):
+        ts = [s._dtmin_tensor(k) for s in self.sols]
+        m = self.torch.stack([t.reshape(()) for t in ts]).min()
+        for t in ts:
+            t.fill_(m)
+        self._sync()
+
+    def advance_batch(self, steps, overlap=True):
+        """same launch sequence per rank as ShardedSolver.advance_batch_async"""
+        L = self.sols[0].L
+        for s in self.sols:
+            B.check(L.amrb_pool_batch_begin(s.pool.h, steps, B.DBL_MAX))
+        self._sync()
+        self._reduce_dtmin(0)
+        for k in range(steps):
+            self.exchange()
+            for s in self.sols:
+                pl, h = s.plan, s.pool.h
+                if overlap:
+                    if len(pl.interior):
+                        B.check(L.amrb_pool_step_partial(h, s.d_interior.data_ptr(), len(pl.interior)))
+                    if len(pl.boundary):
+                        B.check(L.amrb_pool_step_partial(h, s.d_boundary.data_ptr(), len(pl.boundary)))
+                else:
+                    B.check(L.amrb_pool_step_partial(h, None, 0))
+            self._sync()
+            self._reduce_dtmin(k + 1)
+            for s in self.sols:
+                B.check(L.amrb_pool_step_commit(s.pool.h))
+        self.exchange()
+        for s in self.sols:
+            B.check(L.amrb_pool_batch_end(s.pool.h, 1))
+        self._sync()
+        return [s.finish_advance_batch(steps) for s in self.sols]
+
+    def close(self):
+        for s in self.sols:
+            s.pool.close()
 
 
 # ---------------------------------------------------------------------------------------- bench

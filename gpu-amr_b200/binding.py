@@ -90,6 +90,7 @@ def lib():
         "amrb_pool_upload_interior": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_download_interior": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_halo_exchange": [vp],
+        "amrb_pool_swap_buffers": [vp],
         "amrb_pool_set_lazy_halos": [vp, C.c_int],
         "amrb_pool_ensure_halos": [vp],
         "amrb_pool_compute_dt": [vp, C.POINTER(C.c_double)],

@@ -905,6 +905,18 @@ amrb_status amrb_pool_halo_exchange(amrb_pool* p)
     return check_launch(p, "halo_kernel");
 }
 
+// current <-> next, for callers that fill the next buffer themselves (patch migration between the
+// Morton ranges of a sharded mesh writes the incoming patches there); the tables stay as they are
+amrb_status amrb_pool_swap_buffers(amrb_pool* p)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is open");
+    swap_buffers(p);
+    p->carry_valid = false;
+    p->halos_stale = false;
+    return AMRB_OK;
+}
+
 // Lazy materialisation of the face halos (drop-in headers): the fused step never reads stored ghosts, so
 // the post-condition of a reference step "face halos of the current buffer are filled"
 // (amr_solver.hpp:351-352) only has to hold when something OBSERVES the padded patches: a download, the

@@ -71,6 +71,46 @@ class ShardPlan:
         assert (self.recv_entries[:, 0] >= self.n_owned).all()
 
 
+class ReshardPlan:
+    """Re-slicing after a reconstruct.  `kind/src/child` is the transfer plan of
+    amrb_tree_reconstruct over the NEW global leaf order (0 copy of old leaf src, 1 prolongation from
+    old leaf src, 2 restriction of old leaves src .. src+fan-1); old and new order are both Morton
+    order, so the old leaves a rank needs for its new range form ONE contiguous old range [a, b).
+    Phase A moves whole old patches so that rank q holds [a_q, b_q) in slots 0.. of its next buffer
+    (contiguous range copies between ranks that are neighbours on the curve); phase B applies the
+    rank's slice of the plan, re-indexed to a_q, with the single-GPU plan kernel."""
+
+    def __init__(self, old_bounds, new_size, kind, src, child, fan, world):
+        kind, src, child = np.asarray(kind), np.asarray(src, np.int64), np.asarray(child)
+        self.world = world
+        self.old_bounds = np.asarray(old_bounds, np.int64)
+        self.new_bounds = np.array([(r * new_size) // world for r in range(world + 1)], dtype=np.int64)
+        end = src + np.where(kind == 2, fan, 1)
+        assert (np.diff(src) >= 0).all(), "the transfer plan is monotone in Morton order"
+        self.need = []          # [a_q, b_q) per rank
+        self.sub = []           # (kind, src - a_q, child) per rank
+        for q in range(world):
+            lo, hi = int(self.new_bounds[q]), int(self.new_bounds[q + 1])
+            if hi > lo:
+                a, b = int(src[lo:hi].min()), int(end[lo:hi].max())
+            else:
+                a = b = 0
+            self.need.append((a, b))
+            self.sub.append((np.ascontiguousarray(kind[lo:hi], np.int8),
+                             np.ascontiguousarray(src[lo:hi] - a, np.int32),
+                             np.ascontiguousarray(child[lo:hi], np.int8)))
+        # moves[(r, q)] = (first old global index, count): old owner r -> new holder q
+        self.moves = {}
+        for q, (a, b) in enumerate(self.need):
+            for r in range(world):
+                lo, hi = max(int(self.old_bounds[r]), a), min(int(self.old_bounds[r + 1]), b)
+                if hi > lo:
+                    self.moves[(r, q)] = (lo, hi - lo)
+
+    def staging_slots(self, q):
+        return self.need[q][1] - self.need[q][0]
+
+
 def raw_tensor(ptr, n, torch, dtype="<f8"):
     """torch view of device memory owned by the library (e.g. the dt-min slots)."""
 
@@ -86,13 +126,16 @@ def raw_tensor(ptr, n, torch, dtype="<f8"):
 class ShardedSolver:
     """One rank's share of the mesh on one GPU."""
 
-    def __init__(self, cfg, host_tree, rank, world, device, dist, torch):
+    def __init__(self, cfg, host_tree, rank, world, device, dist, torch, capacity=None):
         self.cfg, self.rank, self.world, self.dist, self.torch = cfg, rank, world, dist, torch
+        self.device = device
         levels, rel, nbr, quad = host_tree.tables()
         self.plan = pl = ShardPlan(levels, rel, nbr, quad, rank, world)
         self.ids = host_tree.ids()[pl.lo:pl.hi]
         self.lay = B.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth)
-        self.pool = B.DevicePool(self.lay, max(pl.n_total, 1), device)
+        # capacity: slots for owned + ghost patches; meshes that change need headroom
+        self.capacity = max(pl.n_total, 1) if capacity is None else int(capacity)
+        self.pool = B.DevicePool(self.lay, self.capacity, device)
         self.pool.set_physics([cfg.length] * 3, cfg.gamma, cfg.cfl)
         self.pool.set_topology(pl.levels, pl.rel, pl.nbr, pl.quad, n_total=pl.n_total)
         self.L = B.lib()
@@ -108,6 +151,12 @@ class ShardedSolver:
             self.ar_group = dist.new_group(ranks=list(range(world)))
         self.graphs = {}
         self._dtmin_cache = {}
+        self.launches = 0
+        self._install_exchange()
+
+    def _install_exchange(self):
+        """device copies of the plan's entry lists and the slab buffers (after every new ShardPlan)"""
+        torch, pl, cfg, device = self.torch, self.plan, self.cfg, self.device
         slab = self.L.amrb_pool_face_slab_doubles(self.pool.h, 0) * cfg.nvar
         self.slab = slab
         dev = torch.device("cuda", device)
@@ -120,7 +169,31 @@ class ShardedSolver:
         self.in_splits = [int(c * slab) for c in pl.send_counts]
         self.out_splits = [int(c * slab) for c in pl.recv_counts]
         self.exchanged_bytes = (sum(self.in_splits) + sum(self.out_splits)) * 8
-        self.launches = 0
+        self.graphs = {}
+        self._dtmin_cache = {}
+
+    # ---- re-slicing after a reconstruct
+    def field_views(self, which):
+        """torch views of the whole current ('cur') / next ('nxt') field arrays of the pool"""
+        get = self.L.amrb_pool_field if which == "cur" else self.L.amrb_pool_next_field
+        n = self.capacity * self.pool.flat
+        return [raw_tensor(get(self.pool.h, f), n, self.torch) for f in range(self.cfg.nvar)]
+
+    def finish_reshard(self, rp, new_host_tree):
+        """phase B: the incoming old patches [a, b) sit in the next buffer -> make them current, apply
+        this rank's slice of the transfer plan, install the new ShardPlan (tables, ghost slots)"""
+        B.check(self.L.amrb_pool_swap_buffers(self.pool.h))
+        kind, src, child = rp.sub[self.rank]
+        if len(kind):
+            self.pool.apply_plan(kind, src, child)
+        levels, rel, nbr, quad = new_host_tree.tables()
+        self.plan = pl = ShardPlan(levels, rel, nbr, quad, self.rank, self.world)
+        if pl.n_total > self.capacity or rp.staging_slots(self.rank) > self.capacity:
+            raise B.AmrbError("shard of %d patches (+ghosts) exceeds the pool capacity %d"
+                              % (pl.n_total, self.capacity))
+        self.ids = new_host_tree.ids()[pl.lo:pl.hi]
+        self.pool.set_topology(pl.levels, pl.rel, pl.nbr, pl.quad, n_total=pl.n_total)
+        self._install_exchange()
 
     # ---- data
     def upload_interior(self, data):
@@ -251,9 +324,13 @@ class LocalCluster:
     copies.  Test vehicle for the sharding logic on a single-GPU box (the NCCL transport itself is
     covered by tests/test_multigpu_gpu.py on >= 2 GPUs)."""
 
-    def __init__(self, cfg, host_tree, world, device, torch):
+    def __init__(self, cfg, host_tree, world, device, torch, capacity=None):
         self.torch, self.world, self.cfg = torch, world, cfg
-        self.sols = [ShardedSolver(cfg, host_tree, r, world, device, None, torch) for r in range(world)]
+        self.sols = [ShardedSolver(cfg, host_tree, r, world, device, None, torch, capacity=capacity)
+                     for r in range(world)]
+        self._index_exchange()
+
+    def _index_exchange(self):
         # where rank r's send segment for rank q starts / where q expects r's data
         self.send_off = [np.concatenate([[0], np.cumsum(s.in_splits)]).astype(int) for s in self.sols]
         self.recv_off = [np.concatenate([[0], np.cumsum(s.out_splits)]).astype(int) for s in self.sols]
@@ -319,6 +396,35 @@ class LocalCluster:
             B.check(L.amrb_pool_batch_end(s.pool.h, 1))
         self._sync()
         return [s.finish_advance_batch(steps) for s in self.sols]
+
+    def patch_max_flags(self, field, refine_thr, coarsen_thr, min_level, max_level):
+        """the criterion on every shard, concatenated in global (Morton) order"""
+        out = [s.pool.patch_max_flags(field, refine_thr, coarsen_thr, min_level, max_level)[:s.plan.n_owned]
+               for s in self.sols]
+        return np.concatenate(out)
+
+    def reshard(self, host_tree, old_size, plan):
+        """after host_tree.reconstruct(): move old patches to the ranks that need them (phase A, here
+        device-to-device copies; the NCCL form sends the same contiguous ranges), then every shard
+        applies its slice of the plan and installs its new tables (phase B)"""
+        kind, src, child = plan
+        flat = self.sols[0].pool.flat
+        old_bounds = [s.plan.lo for s in self.sols] + [old_size]
+        rp = ReshardPlan(old_bounds, host_tree.size, kind, src, child, 1 << self.cfg.rank, self.world)
+        self.halo_exchange()                    # copied patches carry their halos along
+        cur = [s.field_views("cur") for s in self.sols]
+        nxt = [s.field_views("nxt") for s in self.sols]
+        for (r, q), (first, count) in rp.moves.items():
+            so = (first - int(old_bounds[r])) * flat
+            do = (first - rp.need[q][0]) * flat
+            for f in range(self.cfg.nvar):
+                nxt[q][f][do:do + count * flat].copy_(cur[r][f][so:so + count * flat])
+        self._sync()
+        for s in self.sols:
+            s.finish_reshard(rp, host_tree)
+        self._index_exchange()
+        self._sync()
+        return rp
 
     def close(self):
         for s in self.sols:

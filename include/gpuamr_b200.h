@@ -110,6 +110,9 @@ void*       amrb_pool_stream(const amrb_pool* pool);
 /* current-buffer device pointer of field f (ndtree::get_device_buffer, ndtree.hpp:561-581) */
 double*     amrb_pool_field(const amrb_pool* pool, int field);
 double*     amrb_pool_next_field(const amrb_pool* pool, int field);
+/* current <-> next (ndtree::swap_buffers, ndtree.hpp:1558-1579) for callers that filled the next buffer
+ * themselves, e.g. patch migration between the Morton ranges of a sharded mesh */
+amrb_status amrb_pool_swap_buffers(amrb_pool* pool);
 
 /* neighbor / halo index tables in the reference's host form, one row per (patch, direction):
  *   levels[P]; rel[P][2R]; nbr[P][2R][2^(R-1)] (linear patch index, -1 padded);

@@ -91,3 +91,74 @@ def test_sharding_logic_in_one_process(case, world):
             assert acc == acc1 and n == n1 and np.array_equal(np.asarray(dts), np.asarray(dts1))
     cl.close()
     pool.close()
+
+
+@pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 3)])
+def test_reslicing_after_reconstruct_in_one_process(case, world):
+    """Active AMR on a sharded mesh, on ONE GPU through LocalCluster: steps, the criterion
+    on every shard, one global reconstruct (refine + coarsen + 2:1 ripple), re-slicing — old patches move
+    to the ranks that need them, every shard applies its slice of the transfer plan and installs its new
+    tables and ghost slots — and more steps.  Leaf ids, flags, state and dt sequence must be identical to
+    the single-pool DeviceTree doing the same."""
+    import importlib
+
+    import numpy as np
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    amrb = importlib.import_module("gpu-amr_b200")
+    mg = importlib.import_module("gpu-amr_b200.multigpu")
+    wl = importlib.import_module("gpu-amr_b200.workloads")
+    if case == "2d":
+        cfg = wl.Config(2, 16, 1, 7, amrb.EQ_EULER)
+        base, radii, thr = 3, (0.3, 0.15), (0.62, 0.52)
+    else:
+        cfg = wl.Config(3, 8, 1, 5, amrb.EQ_EULER)
+        base, radii, thr = 2, (0.3,), (0.62, 0.52)
+    steps, cap = 4, 4096
+
+    # single pool (the checker of this test)
+    one = amrb.DeviceTree(cfg, capacity=cap)
+    host0 = wl.build_static_tree(cfg, base, radii)
+    # replay the same refinement history on the DeviceTree's own host tree
+    for _ in range(base):
+        one.reconstruct(wl.flags_refine_all(one.ids()))
+    for i, r in enumerate(radii):
+        one.reconstruct(wl.flags_ball(one.ids(), cfg, r, base + i + 1, (0.5, 0.5, 0.5)))
+    assert np.array_equal(one.ids(), host0.ids())
+    ic = wl.initial_condition(one.ids(), cfg)
+    one.set_interior(ic)
+    one.halo_exchange()
+    ref_a = one.advance_batch(steps)
+    flags1 = one.pool.patch_max_flags(0, thr[0], thr[1], 1, cfg.depth if case == "2d" else 4)
+
+    # W shards in this process
+    host = wl.build_static_tree(cfg, base, radii)
+    cl = mg.LocalCluster(cfg, host, world, 0, torch, capacity=cap)
+    for s in cl.sols:
+        s.upload_interior(wl.initial_condition(s.ids, cfg))
+    cl.halo_exchange()
+    out_a = cl.advance_batch(steps)
+    flags = cl.patch_max_flags(0, thr[0], thr[1], 1, cfg.depth if case == "2d" else 4)
+    assert np.array_equal(flags, flags1) and (flags == 1).any() and (flags == 2).any()
+
+    old_size = host.size
+    assert host.reconstruct(flags, cap) == 1
+    assert one.reconstruct(flags1) == 1
+    assert np.array_equal(host.ids(), one.ids()) and host.size != old_size
+    rp = cl.reshard(host, old_size, host.plan())
+    if case == "2d":
+        assert any(r != q for (r, q) in rp.moves), "this case moves patches between ranks"
+    cl.halo_exchange()
+    one.halo_exchange()
+    out_b = cl.advance_batch(steps)
+    ref_b = one.advance_batch(steps)
+
+    got = np.concatenate([s.download_interior().reshape(cfg.nvar, -1, cfg.data) for s in cl.sols], axis=1)
+    ref = one.get_interior().reshape(cfg.nvar, -1, cfg.data)
+    assert np.array_equal(got, ref)
+    for per_rank, (acc1, n1, dts1) in ((out_a, ref_a), (out_b, ref_b)):
+        for acc, n, dts in per_rank:
+            assert acc == acc1 and n == n1 and np.array_equal(np.asarray(dts), np.asarray(dts1))
+    cl.close()

@@ -137,3 +137,48 @@ def test_two_process_slab_exchange_gloo(amrb):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res) and all(n > 0 for _, _, n in res), res
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("cfgname", ["r2_s8_h1_d7_euler", "r3_s4_h1_d5_euler"])
+def test_reshard_plan_moves_every_needed_patch_once(amrb, world, cfgname):
+    """Re-slicing after a reconstruct, host logic: with the old leaves spread over W
+    Morton ranges and a refine + coarsen pass applied, (1) the old leaves a rank needs for its new range
+    are one contiguous old range and arrive exactly once, (2) the rank's re-indexed slice of the transfer
+    plan, evaluated on what arrived, reproduces the global plan."""
+    mg = importlib.import_module("gpu-amr_b200.multigpu")
+    cfg, t = _tree(amrb, cfgname)
+    old_ids = t.ids()
+    n_old = len(old_ids)
+    # Morton-contiguous blocks keep sibling families together: merge in the first half of the curve,
+    # split in the last quarter
+    flags = np.zeros(n_old, np.int8)
+    flags[:n_old // 2] = amrb.COARSEN
+    flags[-(n_old // 4):] = amrb.REFINE
+    assert t.reconstruct(flags) == 1
+    kind, src, child = t.plan()
+    n_new, fan = t.size, 1 << cfg.rank
+    assert (kind == 2).any() and (kind == 1).any() and (kind == 0).any()
+    old_bounds = [(r * n_old) // world for r in range(world + 1)]
+    rp = mg.ReshardPlan(old_bounds, n_new, kind, src, child, fan, world)
+
+    def evaluate(k, s, c, payload):                  # what a new patch is made of, symbolically
+        return ("copy", payload[s]) if k == 0 else ("prolong", payload[s], int(c)) if k == 1 else \
+               ("restrict", tuple(payload[s:s + fan]))
+
+    want = [evaluate(kind[j], src[j], child[j], np.arange(n_old)) for j in range(n_new)]
+    got = []
+    for q in range(world):
+        a, b = rp.need[q]
+        staged = np.full(b - a, -1, np.int64)        # old global index held by every staging slot
+        for (r, qq), (first, count) in rp.moves.items():
+            if qq != q:
+                continue
+            assert old_bounds[r] <= first and first + count <= old_bounds[r + 1]
+            assert (staged[first - a:first - a + count] == -1).all()
+            staged[first - a:first - a + count] = np.arange(first, first + count)
+        assert (staged >= 0).all()
+        ks, ss, cs = rp.sub[q]
+        assert len(ks) == rp.new_bounds[q + 1] - rp.new_bounds[q]
+        got += [evaluate(ks[j], ss[j], cs[j], staged) for j in range(len(ks))]
+    assert got == want

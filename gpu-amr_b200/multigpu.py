@@ -111,6 +111,28 @@ class ReshardPlan:
         return self.need[q][1] - self.need[q][0]
 
 
+def migrate_old_patches(rp, rank, flat, cur, nxt, dist):
+    """Phase A of the re-slicing over torch.distributed point-to-point operations (NCCL between GPUs,
+    gloo in the CPU test): cur[f] / nxt[f] are flat views of this rank's current / next field arrays
+    (device or host tensors); the old patches [a, b) this rank needs end up in nxt[f][0 : (b-a)*flat].
+    Both sides walk the moves in the same (sender, receiver, field) order."""
+    a, lo = rp.need[rank][0], int(rp.old_bounds[rank])
+    ops = []
+    for (r, q), (first, count) in sorted(rp.moves.items()):
+        n = count * flat
+        so, do = (first - lo) * flat, (first - a) * flat
+        if r == rank and q == rank:
+            for f in range(len(cur)):
+                nxt[f][do:do + n].copy_(cur[f][so:so + n])
+        elif r == rank:
+            ops += [dist.P2POp(dist.isend, cur[f][so:so + n], q) for f in range(len(cur))]
+        elif q == rank:
+            ops += [dist.P2POp(dist.irecv, nxt[f][do:do + n], r) for f in range(len(cur))]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 def raw_tensor(ptr, n, torch, dtype="<f8"):
     """torch view of device memory owned by the library (e.g. the dt-min slots)."""
 
@@ -178,6 +200,22 @@ class ShardedSolver:
         get = self.L.amrb_pool_field if which == "cur" else self.L.amrb_pool_next_field
         n = self.capacity * self.pool.flat
         return [raw_tensor(get(self.pool.h, f), n, self.torch) for f in range(self.cfg.nvar)]
+
+    def reshard(self, new_host_tree, old_size, plan):
+        """re-slicing after new_host_tree.reconstruct() (every rank ran it on the same global flags):
+        phase A over NCCL point-to-point copies, phase B locally.  The two phases are tested
+        separately (migrate_old_patches over gloo on the CPU, finish_reshard through LocalCluster on
+        one GPU); their composition has not been run on several GPUs yet."""
+        kind, src, child = plan
+        old_bounds = [(r * old_size) // self.world for r in range(self.world + 1)]
+        rp = ReshardPlan(old_bounds, new_host_tree.size, kind, src, child, 1 << self.cfg.rank, self.world)
+        self.halo_exchange()                    # copied patches carry their halos along
+        self.torch.cuda.synchronize()
+        migrate_old_patches(rp, self.rank, self.pool.flat, self.field_views("cur"),
+                            self.field_views("nxt"), self.dist)
+        self.torch.cuda.synchronize()
+        self.finish_reshard(rp, new_host_tree)
+        return rp
 
     def finish_reshard(self, rp, new_host_tree):
         """phase B: the incoming old patches [a, b) sit in the next buffer -> make them current, apply

@@ -182,3 +182,59 @@ def test_reshard_plan_moves_every_needed_patch_once(amrb, world, cfgname):
         assert len(ks) == rp.new_bounds[q + 1] - rp.new_bounds[q]
         got += [evaluate(ks[j], ss[j], cs[j], staged) for j in range(len(ks))]
     assert got == want
+
+
+def _reshard_worker(rank, world, port, cfgname, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        amrb = importlib.import_module("gpu-amr_b200")
+        mg = importlib.import_module("gpu-amr_b200.multigpu")
+        cfg, t = _tree(amrb, cfgname)
+        n_old = t.size
+        flags = np.zeros(n_old, np.int8)
+        flags[:n_old // 2] = amrb.COARSEN
+        flags[-(n_old // 4):] = amrb.REFINE
+        assert t.reconstruct(flags) == 1
+        kind, src, child = t.plan()
+        old_bounds = [(r * n_old) // world for r in range(world + 1)]
+        rp = mg.ReshardPlan(old_bounds, t.size, kind, src, child, 1 << cfg.rank, world)
+        flat, nv = 6, 2                                             # tiny stand-in patches
+        glob = [np.arange(n_old * flat, dtype=np.float64) + 1e6 * f for f in range(nv)]
+        lo, hi = old_bounds[rank], old_bounds[rank + 1]
+        cap = max(hi - lo, rp.staging_slots(rank)) + 4
+        cur = [torch.zeros(cap * flat, dtype=torch.float64) for _ in range(nv)]
+        nxt = [torch.full((cap * flat,), -1.0, dtype=torch.float64) for _ in range(nv)]
+        for f in range(nv):
+            cur[f][:(hi - lo) * flat] = torch.from_numpy(glob[f][lo * flat:hi * flat])
+        mg.migrate_old_patches(rp, rank, flat, cur, nxt, dist)
+        a, b = rp.need[rank]
+        ok = all(np.array_equal(nxt[f][:(b - a) * flat].numpy(), glob[f][a * flat:b * flat]) for f in range(nv))
+        moved = sum(c for (r, qq), (_, c) in rp.moves.items() if qq == rank and r != rank)
+        q.put((rank, bool(ok), int(moved)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_patch_migration_over_gloo(amrb):
+    """phase A of the re-slicing (contiguous old ranges between Morton neighbours) over
+    torch.distributed point-to-point operations, 3 processes, gloo"""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reshard_worker, args=(r, 3, port, "r2_s8_h1_d7_euler", q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(n for _, _, n in res) > 0, "the case must move patches between ranks"

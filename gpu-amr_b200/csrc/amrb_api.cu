@@ -399,8 +399,7 @@ void fill_step_args(const amrb_pool* p, StepArgs& a)
         static const int tm = getenv("AMRB_TASKMAP") ? atoi(getenv("AMRB_TASKMAP")) : 1;
         a.task_map = tm;
     }
-    a.queue       = nullptr;
-    a.queue_reset = nullptr;
+    a.queue     = nullptr;
     a.gamma     = p->gamma;
     std::memcpy(a.dx, p->dx, sizeof(a.dx));
     a.sc = StepScalars{ nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, p->cfl };

@@ -372,8 +372,8 @@ struct StepArgs
                               // 0 = contiguous task range per CTA
     unsigned int*  queue;       // optional dynamic task counter of THIS launch (3D marching kernel):
                                 // a warp takes its next task when it finishes one, so warps slowed
-                                // down by coarse/fine faces do not drift out of the common window
-    unsigned int*  queue_reset; // unused (the host zeroes the counter in stream order)
+                                // down by coarse/fine faces do not drift out of the common window;
+                                // zeroed by the host in stream order before the launch
     double         gamma;
     double         dx[kMaxLevel + 1][3]; // per level, per solver direction (x,y,z)
     StepScalars    sc;

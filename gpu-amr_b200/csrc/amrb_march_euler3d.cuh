@@ -4,11 +4,17 @@
 //   * task = one 8 x 8 (x, y) column block of one patch, all S planes along z (the slowest layout
 //     dim); an 8^3 patch is one task, a 16^3 patch four.  A warp walks its tasks back to back and
 //     never meets a block barrier.
-//   * the planes of a task stream through a warp-private shared-memory ring of NS stages filled by
-//     TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): for 8^3 patches one copy per
-//     field moves CR whole padded planes (contiguous in the pool), for wider patches one copy per
-//     field-plane moves the block's 8 padded rows.  Only the S interior planes are streamed; the
-//     ghost planes below / above are never read from the pool.
+//   * the planes of a task stream through a warp-private shared-memory ring of NS stages: for 8^3
+//     patches TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), one per field moving CR
+//     whole padded planes (contiguous in the pool); for wider patches the block's 8 padded rows of
+//     a field-plane are too small for a warp's bulk-copy rate (tools/tma_bench.cu), so all lanes
+//     move 16-byte cp.async pieces and arrive on the stage's mbarrier.  Only the S interior planes
+//     are streamed; the ghost planes below / above are never read from the pool.
+//   * tasks: the first one of a warp is static (warp w of W takes task w: the chip starts on one
+//     Morton window), every further one is drawn from a device counter, so that warps slowed down
+//     by coarse/fine faces do not drift out of the window and ghost gathers keep hitting L2; the
+//     halo tables of the NEXT task are fetched one 32-bit piece per lane while the current task is
+//     marched and handed round by shuffles.
 //   * lane = (y row 0..7) x (x pair 0..3): a lane owns two x-adjacent cells of the plane and marches
 //     them along z.  The cell record (U, p, a, 1/rho) is derived once, in registers; the z-face
 //     flux is carried in registers (folded into the running update); x-faces as in 2D (left

@@ -194,11 +194,52 @@ struct amrb_tree
 
 extern "C" {
 
+// bit interleave by shift-and-mask (21 bits per coordinate): x in bit 0 of every group
+static inline uint64_t spread2(uint64_t v)
+{
+    v &= 0x1fffffull;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+static inline uint32_t gather2(uint64_t v)
+{
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v >> 4)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v >> 8)) & 0x0000ffff0000ffffull;
+    v = (v | (v >> 16)) & 0x00000000ffffffffull;
+    return (uint32_t)v;
+}
+static inline uint64_t spread3(uint64_t v)
+{
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+static inline uint32_t gather3(uint64_t v)
+{
+    v &= 0x1249249249249249ull;
+    v = (v | (v >> 2)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v >> 4)) & 0x100f00f00f00f00full;
+    v = (v | (v >> 8)) & 0x1f0000ff0000ffull;
+    v = (v | (v >> 16)) & 0x1f00000000ffffull;
+    v = (v | (v >> 32)) & 0x1fffffull;
+    return (uint32_t)v;
+}
+
 uint64_t amrb_morton_encode(int rank, const uint32_t* c, int level)
 {
-    uint64_t m = 0;
-    for (int b = 0; b < 20; ++b)
-        for (int a = 0; a < rank; ++a) m |= (uint64_t)((c[a] >> b) & 1u) << (rank * b + a);
+    const uint64_t m = (rank == 2) ? (spread2(c[0]) | (spread2(c[1]) << 1))
+                                   : (spread3(c[0]) | (spread3(c[1]) << 1) | (spread3(c[2]) << 2));
     return (m << kLevelBits) | (uint64_t)level;
 }
 
@@ -206,9 +247,17 @@ void amrb_morton_decode(int rank, uint64_t id, uint32_t* c, int* level)
 {
     if (level) *level = (int)(id & ((1u << kLevelBits) - 1));
     const uint64_t m = id >> kLevelBits;
-    for (int a = 0; a < rank; ++a) c[a] = 0;
-    for (int b = 0; b < 20; ++b)
-        for (int a = 0; a < rank; ++a) c[a] |= (uint32_t)((m >> (rank * b + a)) & 1ull) << b;
+    if (rank == 2)
+    {
+        c[0] = gather2(m);
+        c[1] = gather2(m >> 1);
+    }
+    else
+    {
+        c[0] = gather3(m);
+        c[1] = gather3(m >> 1);
+        c[2] = gather3(m >> 2);
+    }
 }
 
 amrb_status amrb_tree_create(int rank, int depth, amrb_tree** out)

@@ -8,4 +8,4 @@ importlib.import_module("gpu-amr_b200") (the hyphen comes from the reference's r
 """
 from .binding import (AmrbError, DevicePool, DeviceTree, HostTree, Layout, build, check,  # noqa: F401
                       declared_symbols, lib, make_layout, EQ_ADVECTION, EQ_EULER, STABLE, REFINE,
-                      COARSEN, DBL_MAX, LIB_PATH)
+                      COARSEN, DBL_MAX, LIB_PATH, STORAGE_PADDED, STORAGE_INTERIOR)

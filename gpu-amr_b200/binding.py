@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libgpuamr_b200.so")
 HEADER = os.path.join(ROOT, "include", "gpuamr_b200.h")
 
 EQ_ADVECTION, EQ_EULER = 0, 1
+STORAGE_PADDED, STORAGE_INTERIOR = 0, 1
 STABLE, REFINE, COARSEN = 0, 1, 2
 DBL_MAX = 1.7976931348623157e308
 
@@ -30,7 +31,8 @@ class AmrbError(RuntimeError):
 
 class Layout(C.Structure):
     _fields_ = [("rank", C.c_int32), ("size", C.c_int32 * 3), ("halo", C.c_int32),
-                ("nvar", C.c_int32), ("equation", C.c_int32), ("depth", C.c_int32)]
+                ("nvar", C.c_int32), ("equation", C.c_int32), ("depth", C.c_int32),
+                ("storage", C.c_int32)]
 
 
 def build(verbose=False):
@@ -98,6 +100,8 @@ def lib():
         "amrb_pool_advance_batch_async": [vp, sz, C.c_double],
         "amrb_pool_finish_advance_batch": [vp, C.POINTER(C.c_double), C.POINTER(sz), dp, sz],
         "amrb_pool_set_mode": [vp, C.c_int],
+        "amrb_pool_set_variant": [vp, C.c_int],
+        "amrb_pool_mark_dirty": [vp],
         "amrb_pool_batch_begin": [vp, sz, C.c_double],
         "amrb_pool_step_partial": [vp, i32p, sz],
         "amrb_pool_step_commit": [vp],
@@ -123,7 +127,7 @@ def lib():
         fn.restype = C.c_int
     L.amrb_layout_supported.argtypes = [C.POINTER(Layout)]
     L.amrb_layout_supported.restype = C.c_int
-    for name in ("amrb_layout_flat_size", "amrb_layout_data_size"):
+    for name in ("amrb_layout_flat_size", "amrb_layout_data_size", "amrb_layout_storage_size"):
         getattr(L, name).argtypes = [C.POINTER(Layout)]
         getattr(L, name).restype = sz
     for name in ("amrb_pool_capacity", "amrb_pool_size", "amrb_tree_size", "amrb_tree_plan_size"):
@@ -157,9 +161,9 @@ def check(status):
         raise AmrbError("amrb status %d: %s" % (status, lib().amrb_last_error().decode()))
 
 
-def make_layout(rank, size, halo, eq, depth):
+def make_layout(rank, size, halo, eq, depth, storage=STORAGE_PADDED):
     lay = Layout()
-    lay.rank, lay.halo, lay.equation, lay.depth = rank, halo, eq, depth
+    lay.rank, lay.halo, lay.equation, lay.depth, lay.storage = rank, halo, eq, depth, storage
     for k in range(3):
         lay.size[k] = size if k < rank else 1
     lay.nvar = 1 if eq == EQ_ADVECTION else rank + 2
@@ -222,8 +226,9 @@ class DevicePool:
     def __init__(self, lay, capacity, device=0, external=None, stream=None):
         self.L = lib()
         self.lay = lay
-        self.flat = self.L.amrb_layout_flat_size(C.byref(lay))
+        self.flat = self.L.amrb_layout_flat_size(C.byref(lay))      # padded patch (host exchange format)
         self.data = self.L.amrb_layout_data_size(C.byref(lay))
+        self.stored = self.L.amrb_layout_storage_size(C.byref(lay))  # doubles per field-patch in the pool
         h = C.c_void_p()
         if external is None:
             check(self.L.amrb_pool_create(C.byref(lay), capacity, device, C.byref(h)))
@@ -315,6 +320,12 @@ class DevicePool:
     def set_mode(self, mode):
         check(self.L.amrb_pool_set_mode(self.h, mode))
 
+    def set_variant(self, variant):
+        check(self.L.amrb_pool_set_variant(self.h, variant))
+
+    def mark_dirty(self):
+        check(self.L.amrb_pool_mark_dirty(self.h))
+
     def apply_plan(self, kind, src, child):
         check(self.L.amrb_pool_apply_plan(self.h, len(kind), _ptr(kind), _ptr(src), _ptr(child)))
 
@@ -335,9 +346,9 @@ class DeviceTree:
     """HostTree + DevicePool behind the interface the oracle's script runner drives
     (same method names as oracle.OracleTree, which mirrors ndtree + amr_solver)."""
 
-    def __init__(self, cfg, capacity=20000, device=0, mode=0):
+    def __init__(self, cfg, capacity=20000, device=0, mode=0, storage=STORAGE_PADDED):
         self.cfg = cfg
-        self.lay = make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth)
+        self.lay = make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage)
         self.tree = HostTree(cfg.rank, cfg.depth)
         self.pool = DevicePool(self.lay, capacity, device)
         self.pool.set_physics([cfg.length] * 3, cfg.gamma, cfg.cfl)

@@ -1,0 +1,247 @@
+// Fused advection step over the interior-only 3D pool layout (amrb_layout.storage = AMRB_STORAGE_INTERIOR).
+//
+// Scalar advection moves 16 algorithmic bytes per cell update and ~20 flops: a pure streaming kernel.
+//   * AdvectionPhysics<3> has velocity {1, 0.5, 0} (include/solver/AdvectionPhysics.hpp:24): no motion
+//     along z, the z-face fluxes are exactly zero -> planes are independent.  task = 512 cells = ZT whole
+//     planes of one patch (an 8^3 patch is one task, a 16^3 patch eight), one 4 KB TMA bulk copy
+//     (cp.async.bulk + mbarrier complete_tx) into a warp-private double buffer; a warp walks its tasks
+//     back to back and never meets a block barrier; the copy of task k+1 is in flight while task k is
+//     computed.
+//   * the 4 x S x ZT lateral ghost cells of task k+1 are gathered from the neighbor patch INTERIORS through
+//     the halo tables (same / coarser injection: per-lane 8-byte cp.async, no register staging; finer:
+//     the 8-cell mean in the reference's summation order) into a second double buffer while task k is
+//     computed; ghost cells are never written to the pool.
+//   * a lane owns two x-adjacent cells; the x-neighbors are the adjacent lanes' cells (warp shuffles), the
+//     y-neighbors come from the staged plane; stores are 16-byte pairs, 512 contiguous bytes per warp
+//     instruction, every sector fully written.
+// Arithmetic: AdvectionPhysics.hpp:45-66 (Rusanov), amr_solver.hpp:265-353 (update order), expression for
+// expression the thread-per-cell step_kernel (amrb_kernels.cuh).
+#pragma once
+#include "amrb_march_euler3d.cuh"
+
+namespace amrb
+{
+
+template <int S, int WPC>
+struct Adv3DenseCfg
+{
+    static constexpr int SS    = S * S;
+    static constexpr int N     = S * S * S;
+    static constexpr int TASK  = 512;            // cells per task
+    static constexpr int ZT    = TASK / SS;      // planes per task
+    static constexpr int NB    = S / ZT;         // tasks per patch
+    static constexpr int HP    = S / 2;          // pairs per row
+    static constexpr int GH    = 4 * S * ZT;     // ghost cells per task: [side][plane][tangential]
+    static constexpr int WARP_DOUBLES = 2 * TASK + 2 * GH;
+    static constexpr size_t SMEM      = (size_t)WPC * WARP_DOUBLES * sizeof(double);
+    static_assert(S == 8 || S == 16, "512-cell tasks of whole planes");
+};
+
+template <int S, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
+{
+    using C          = Adv3DenseCfg<S, WPC>;
+    constexpr int SS = C::SS, N = C::N, ZT = C::ZT, HP = C::HP, GH = C::GH, HF = S / 2;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[WPC * 2];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double*   ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::WARP_DOUBLES;
+    double*   sG   = ring + 2 * C::TASK;
+    uint64_t* bar  = bars + warp * 2;
+    const double* __restrict__ cur = a.cur.p[0];
+    double* __restrict__       nxt = a.nxt.p[0];
+
+    const int n_tasks = n_items * C::NB;
+    const int gw = blockIdx.x * WPC + warp, nw_all = gridDim.x * WPC;
+    const int nt = (n_tasks > gw) ? (n_tasks - gw + nw_all - 1) / nw_all : 0;
+
+    auto task_of = [&](int k, int& p, int& z0) {
+        const int tau  = gw + k * nw_all;
+        const int item = tau / C::NB;
+        z0             = (tau % C::NB) * ZT;
+        p              = a.list ? a.list[item] : item;
+    };
+
+    if (lane == 0)
+    {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+    }
+    __syncwarp();
+
+    // request task k: the bulk copy of its planes and the gather of its lateral ghost cells
+    auto request = [&](int k) {
+        if (k >= nt) return;
+        int p, z0;
+        task_of(k, p, z0);
+        const int b = k & 1;
+        if (lane == 0)
+        {
+            mbar_expect_tx(&bar[b], C::TASK * 8);
+            bulk_g2s(ring + b * C::TASK, cur + (size_t)p * N + (size_t)z0 * SS, C::TASK * 8, &bar[b]);
+        }
+        double* gdst = sG + b * GH;
+#pragma unroll
+        for (int e = lane; e < GH; e += 32)
+        {
+            const int sd = e / (S * ZT), r = e % (S * ZT), zl = r / S, t = r % S;
+            const int d  = (sd < 2) ? 4 + sd : sd;      // tree direction: x-, x+, y-, y+
+            const int m  = (int)__ldg(a.meta + (size_t)p * 6 + d);
+            const int32_t* nb = a.nbr + ((size_t)p * 6 + d) * 4;
+            const int rel = m & 3;
+            const int z   = z0 + zl;
+            // interior coordinates of the ghost cell mirrored into the neighbor's frame
+            // (patch_utils.hpp:322-327): the normal coordinate -1 -> S-1, S -> 0
+            int fy, fx;
+            if (sd < 2)
+            {
+                fy = t;
+                fx = (sd & 1) ? 0 : S - 1;
+            }
+            else
+            {
+                fx = t;
+                fy = (sd & 1) ? 0 : S - 1;
+            }
+            if (rel == 2)
+            {
+                // finer_t: mean of the 2^3 fine cells of one of the 4 finer neighbors, summed
+                // last-dim-fastest (patch_utils.hpp:334-386, 203-234); finer index = z half + 2 x half of
+                // the other tangential dim (neighbor.hpp:316-337)
+                const int     q = __ldg(nb + (z / HF) + 2 * (t / HF));
+                const double* s = cur + (size_t)q * N + (size_t)((z * 2) % S) * SS + ((fy * 2) % S) * S +
+                                  ((fx * 2) % S);
+                double sum = 0.0;
+                sum += __ldg(s);
+                sum += __ldg(s + 1);
+                sum += __ldg(s + S);
+                sum += __ldg(s + S + 1);
+                sum += __ldg(s + SS);
+                sum += __ldg(s + SS + 1);
+                sum += __ldg(s + SS + S);
+                sum += __ldg(s + SS + S + 1);
+                gdst[e] = sum / 8.0;
+            }
+            else
+            {
+                size_t o;
+                if (rel == 1)
+                    o = (size_t)__ldg(nb) * N + (size_t)z * SS + fy * S + fx; // same_t
+                else if (rel == 3)
+                {
+                    // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
+                    const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
+                    o = (size_t)__ldg(nb) * N + (size_t)(qz * HF + z / 2) * SS + (qy * HF + fy / 2) * S +
+                        (qx * HF + fx / 2);
+                }
+                else
+                {
+                    // relation "none" (never in a periodic balanced tree): the own boundary cell
+                    const int iy = (sd < 2) ? t : ((sd & 1) ? S - 1 : 0);
+                    const int ix = (sd < 2) ? ((sd & 1) ? S - 1 : 0) : t;
+                    o            = (size_t)p * N + (size_t)z * SS + iy * S + ix;
+                }
+                cp_async8(gdst + e, cur + o);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double       rem_after;
+    const double dt = resolve_step_dt(a.sc, rem_after);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.sc.dtmin_in != nullptr)
+    {
+        *a.sc.dt_taken      = dt;
+        *a.sc.remaining_out = rem_after;
+    }
+    double cand = DBL_MAX;
+
+    request(0);
+    for (int k = 0; k < nt; ++k)
+    {
+        request(k + 1); // stage (k+1)&1 was released at the end of task k-1
+        if (k + 1 >= nt) cp_async_commit(); // keep one group per iteration: wait_group<1> below
+        int p, z0;
+        task_of(k, p, z0);
+        const int    b   = k & 1;
+        const int    lvl = __ldg(a.level + p);
+        const double cx = dt / a.dx[lvl][0], cy = dt / a.dx[lvl][1]; // amr_solver.hpp:330
+        // CFL of the next step: speeds are state-independent (AdvectionPhysics.hpp:74-85), z has speed 0
+        cand = fmin(cand, fmin(a.dx[lvl][0] / 1.0, a.dx[lvl][1] / 0.5));
+        mbar_wait(&bar[b], (k >> 1) & 1);
+        cp_async_wait<1>(); // this task's ghosts have landed (the younger group is task k+1's)
+        __syncwarp();
+        const double* pl = ring + b * C::TASK;
+        const double* gh = sG + b * GH;
+        double*       out = nxt + (size_t)p * N + (size_t)z0 * SS;
+#pragma unroll 4
+        for (int it = 0; it < C::TASK / 64; ++it)
+        {
+            const int q  = it * 32 + lane; // pair index inside the task
+            const int x2 = q % HP, y = (q / HP) % S, zl = q / (HP * S);
+            const int o  = zl * SS + y * S + 2 * x2;
+            const double2 c = *reinterpret_cast<const double2*>(pl + o);
+            double        lft = __shfl_up_sync(0xffffffffu, c.y, 1);
+            double        rgt = __shfl_down_sync(0xffffffffu, c.x, 1);
+            if (x2 == 0) lft = gh[(0 * ZT + zl) * S + y];
+            if (x2 == HP - 1) rgt = gh[(1 * ZT + zl) * S + y];
+            const double2 dn = (y > 0) ? *reinterpret_cast<const double2*>(pl + o - S)
+                                       : *reinterpret_cast<const double2*>(gh + (2 * ZT + zl) * S + 2 * x2);
+            const double2 up = (y < S - 1) ? *reinterpret_cast<const double2*>(pl + o + S)
+                                           : *reinterpret_cast<const double2*>(gh + (3 * ZT + zl) * S + 2 * x2);
+            double2 r;
+            {
+                // cell A: left = lft, right = c.y
+                const double u = c.x;
+                double       upd = 0.0;
+                {
+                    const double v = 1.0, uL = lft, uR = c.y;
+                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                    upd -= cx * (fR - fL);
+                }
+                {
+                    const double v = 0.5, uL = dn.x, uR = up.x;
+                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                    upd -= cy * (fR - fL);
+                }
+                r.x = u + upd;
+            }
+            {
+                // cell B: left = c.x, right = rgt
+                const double u = c.y;
+                double       upd = 0.0;
+                {
+                    const double v = 1.0, uL = c.x, uR = rgt;
+                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                    upd -= cx * (fR - fL);
+                }
+                {
+                    const double v = 0.5, uL = dn.y, uR = up.y;
+                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                    upd -= cy * (fR - fL);
+                }
+                r.y = u + upd;
+            }
+            *reinterpret_cast<double2*>(out + o) = r;
+        }
+        __syncwarp(); // every lane is done with stage b and ghost buffer b: task k+2 may overwrite them
+    }
+    cp_async_wait<0>();
+
+    if (a.sc.dtmin_out != nullptr)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = fmin(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0 && nt > 0) atomicMin(a.sc.dtmin_out, (unsigned long long)__double_as_longlong(cand));
+    }
+}
+
+} // namespace amrb

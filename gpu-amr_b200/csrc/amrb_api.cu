@@ -1,6 +1,7 @@
 // C-ABI of the device side: memory/sync wrappers, the device patch pool and all kernel launches.
 // See include/gpuamr_b200.h for the contract and the reference interfaces each group replaces.
 #include "amrb_kernels.cuh"
+#include "amrb_ops.cuh"
 #include "amrb_step_euler.cuh"
 #include "amrb_march_euler.cuh"
 #include "amrb_march_euler3d.cuh"
@@ -10,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cuda_profiler_api.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,24 +44,41 @@ static amrb_status fail(amrb_status code, const std::string& what)
         if (s_ != AMRB_OK) return s_;                                                            \
     } while (0)
 
-// ---------------------------------------------------------------------------------- kernel dispatch
-struct Ops
+// Function attributes (opt-in shared-memory size) and the SM count belong to a DEVICE: a process
+// may open pools on several GPUs, so both are cached per device ordinal (the caller has made the
+// pool's device current).  A failed attribute call is kept for check_launch to report.
+constexpr int kMaxDevices = 64;
+thread_local cudaError_t g_prepare_error = cudaSuccess;
+
+static int current_device()
 {
-    int    rank, size, halo, eq;
-    int    bands;      // CTAs per patch in the fused step
-    size_t step_smem;  // dynamic shared memory of the fused step
-    cudaError_t (*prepare)();
-    void (*halo_fill)(cudaStream_t, const FieldPtrs&, const int32_t*, const uint8_t*, int);
-    void (*step)(cudaStream_t, const StepArgs&, int n_items);
-    void (*step_v1)(cudaStream_t, const StepArgs&, int n_items); // thread-per-cell variant (A/B)
-    void (*compute_dt)(cudaStream_t, const StepArgs&, unsigned long long*);
-    void (*plan)(cudaStream_t, const FieldPtrs&, const FieldPtrs&, const int8_t*, const int32_t*,
-                 const int8_t*, int);
-    void (*flags)(cudaStream_t, const double*, const int32_t*, int, double, double, int, int,
-                  int8_t*);
-    void (*interior)(cudaStream_t, double*, double*, int, int);
-    void (*faces)(cudaStream_t, const FieldPtrs&, const int32_t*, int, double*, int);
-};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+int device_sm_count()
+{
+    static int sms[kMaxDevices] = {};
+    const int  dev = current_device();
+    if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev];
+}
+bool DevicePrepared::ensure(const void* kernel, int smem_bytes)
+{
+    const int dev = current_device();
+    if (done[dev]) return true;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess)
+    {
+        g_prepare_error = e;
+        return false;
+    }
+    done[dev] = true;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------- kernel dispatch
+// struct Ops: amrb_ops.cuh
 
 template <int R, int S, int H, int EQ, int BAND, int EB, int RG, int TPC, int ENT>
 struct Inst
@@ -94,28 +113,14 @@ struct Inst
         step_kernel<R, S, H, EQ, BAND, NT><<<n_items * (S / BAND), NT, SMEM, st>>>(a);
     }
     // warp-autonomous marching kernel (amrb_march_euler.cuh): persistent grid, MINB CTAs per SM
-    static int sm_count()
-    {
-        static int sms = 0;
-        if (sms == 0)
-        {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        }
-        return sms;
-    }
+    static int sm_count() { return device_sm_count(); }
     template <int BANDM, int CR, int NS, int WPC, int MINB>
     static void march(cudaStream_t st, const StepArgs& a, int n_items)
     {
         using MC = March2Cfg<S, H, BANDM, CR, NS, WPC>;
         auto k   = euler2d_march_kernel<S, H, BANDM, CR, NS, WPC, MINB>;
-        static bool prepared = false;
-        if (!prepared)
-        {
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MC::SMEM);
-            prepared = true;
-        }
+        static DevicePrepared prepared;
+        if (!prepared.ensure((const void*)k, (int)MC::SMEM)) return;
         const int tasks = n_items * MC::NB;
         const int grid  = std::max(1, std::min(sm_count() * MINB, (tasks + WPC - 1) / WPC));
         k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
@@ -147,12 +152,8 @@ struct Inst
     {
         using MC = March3Cfg<S, H, CR, NS, WPC>;
         auto k   = euler3d_march_kernel<S, H, CR, NS, WPC, MINB, CPRING>;
-        static bool prepared = false;
-        if (!prepared)
-        {
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MC::SMEM);
-            prepared = true;
-        }
+        static DevicePrepared prepared;
+        if (!prepared.ensure((const void*)k, (int)MC::SMEM)) return;
         const int tasks = n_items * MC::NB;
         const int grid  = std::max(1, std::min(sm_count() * MINB, (tasks + WPC - 1) / WPC));
         k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
@@ -165,7 +166,7 @@ struct Inst
             // of per-lane cp.async row blocks for 16^3); 11 = 1-plane chunks, 4 stages; 14/15 = cp.async ring for
             // 8^3 as well (2-plane / 1-plane chunks); 10 = block-cooperative
             // pipeline (second generation)
-            static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
+            const int v = a.variant;
             if (v != 10)
             {
                 if (v == 11)
@@ -183,7 +184,7 @@ struct Inst
         {
             // AMRB_VARIANT: 0 = marching kernel, band chosen per launch (default); 1/2/3 = marching
             // kernel with 16/32/64-row bands; 10 = block-cooperative pipeline (second generation)
-            static const int v = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
+            const int v    = a.variant;
             const int band = (v == 1) ? 16 : (v == 2) ? 32 : (v == 3) ? 64 : pick_band(n_items);
             if (v != 10)
             {
@@ -240,8 +241,8 @@ struct Inst
     }
     static constexpr Ops ops()
     {
-        return Ops{ R,     S,        H,           EQ,    S / BAND, SMEM,      &prepare, &halo_fill,
-                    &step, &step_v1, &compute_dt, &plan, &flags,   &interior, &faces };
+        return Ops{ R,     S,        H,           EQ,    0,      S / BAND,  SMEM,   &prepare, &halo_fill,
+                    &step, &step_v1, &compute_dt, &plan, &flags, &interior, &faces, nullptr,  nullptr };
     }
 };
 
@@ -277,6 +278,16 @@ static const Ops* find_ops(const amrb_layout& l)
         if (l.size[k] != l.size[0]) return nullptr; // cubic patches only
     const int nv = (l.equation == AMRB_EQ_ADVECTION) ? 1 : l.rank + 2;
     if (l.nvar != nv) return nullptr;
+    if (l.storage == AMRB_STORAGE_INTERIOR)
+    {
+        int        n = 0;
+        const Ops* d = dense_ops(&n);
+        for (int i = 0; i < n; ++i)
+            if (d[i].rank == l.rank && d[i].size == l.size[0] && d[i].halo == l.halo && d[i].eq == l.equation)
+                return &d[i];
+        return nullptr;
+    }
+    if (l.storage != AMRB_STORAGE_PADDED) return nullptr;
     for (const Ops& o : g_ops)
         if (o.rank == l.rank && o.size == l.size[0] && o.halo == l.halo && o.eq == l.equation)
             return &o;
@@ -295,7 +306,10 @@ struct amrb_pool
     int          device   = 0;
     cudaStream_t stream   = nullptr;
     bool         own_stream = false, own_mem = false;
-    size_t       capacity = 0, n_owned = 0, n_total = 0, flat = 0, data = 0;
+    size_t       capacity = 0, n_owned = 0, n_total = 0, data = 0;
+    size_t       flat  = 0; // doubles per field-patch as STORED (padded: prod(size+2h); interior-only: prod(size))
+    size_t       pflat = 0; // doubles per padded field-patch (the host exchange format)
+    bool         dense = false;
     FieldPtrs    cur{}, nxt{};
     int32_t*     d_nbr   = nullptr;
     uint8_t*     d_meta  = nullptr;
@@ -327,6 +341,7 @@ struct amrb_pool
     size_t       plan_cap = 0;
     uint64_t     launches = 0;
     int          mode     = 0;
+    int          variant  = 0; // kernel variant for A/B runs (amrb_pool_set_variant; default AMRB_VARIANT)
 };
 
 namespace
@@ -400,6 +415,7 @@ void fill_step_args(const amrb_pool* p, StepArgs& a)
         a.task_map = tm;
     }
     a.queue     = nullptr;
+    a.variant   = p->variant;
     a.gamma     = p->gamma;
     std::memcpy(a.dx, p->dx, sizeof(a.dx));
     a.sc = StepScalars{ nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, p->cfl };
@@ -407,6 +423,14 @@ void fill_step_args(const amrb_pool* p, StepArgs& a)
 
 amrb_status check_launch(amrb_pool* p, const char* what)
 {
+    if (g_prepare_error != cudaSuccess)
+    {
+        const cudaError_t pe = g_prepare_error;
+        g_prepare_error      = cudaSuccess;
+        cudaGetLastError();
+        return fail(AMRB_ERR_CUDA, std::string(what) + ": cudaFuncSetAttribute(max dynamic shared memory): " +
+                                       cudaGetErrorString(pe));
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     ++p->launches;
@@ -454,8 +478,11 @@ amrb_status pool_alloc_common(const amrb_layout* layout, size_t capacity, int de
     p->ops       = ops;
     p->device    = device;
     p->capacity  = capacity;
-    p->flat      = amrb_layout_flat_size(layout);
+    p->pflat     = amrb_layout_flat_size(layout);
     p->data      = amrb_layout_data_size(layout);
+    p->dense     = layout->storage == AMRB_STORAGE_INTERIOR;
+    p->flat      = p->dense ? p->data : p->pflat;
+    p->variant   = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
     compute_dx(p);
     *out = p;
     return AMRB_OK;
@@ -586,6 +613,10 @@ size_t amrb_layout_flat_size(const amrb_layout* l)
     for (int k = 0; k < l->rank; ++k) n *= (size_t)(l->size[k] + 2 * l->halo);
     return n;
 }
+size_t amrb_layout_storage_size(const amrb_layout* l)
+{
+    return l->storage == AMRB_STORAGE_INTERIOR ? amrb_layout_data_size(l) : amrb_layout_flat_size(l);
+}
 size_t amrb_layout_data_size(const amrb_layout* l)
 {
     size_t n = 1;
@@ -612,8 +643,14 @@ amrb_status amrb_pool_create(const amrb_layout* layout, size_t capacity, int dev
             *out = nullptr;
             return fail(AMRB_ERR_CUDA, "cudaMalloc of the patch pool failed");
         }
-        cudaMemset(p->cur.p[f], 0, bytes);
-        cudaMemset(p->nxt.p[f], 0, bytes);
+        if (cudaMemset(p->cur.p[f], 0, bytes) != cudaSuccess ||
+            cudaMemset(p->nxt.p[f], 0, bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            amrb_pool_destroy(p);
+            *out = nullptr;
+            return fail(AMRB_ERR_CUDA, "cudaMemset of the patch pool failed");
+        }
     }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess)
     {
@@ -693,7 +730,27 @@ uint64_t amrb_pool_launch_count(const amrb_pool* p) { return p ? p->launches : 0
 amrb_status amrb_pool_set_mode(amrb_pool* p, int mode)
 {
     if (!p || mode < 0 || mode > 2) return fail(AMRB_ERR_ARGUMENT, "mode must be 0, 1 or 2");
+    if (p->dense && mode != 0)
+        return fail(AMRB_ERR_UNSUPPORTED, "interior-only pools run the fused step only (modes 1 / 2 need stored ghosts)");
     p->mode = mode;
+    return AMRB_OK;
+}
+
+amrb_status amrb_pool_set_variant(amrb_pool* p, int variant)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    p->variant = variant;
+    return AMRB_OK;
+}
+
+// The caller wrote the current buffer behind the pool's back (through amrb_pool_field /
+// amrb_pool_next_field / get_device_buffer pointers): the dt-min carried over from the last batch
+// describes a state that no longer exists.
+amrb_status amrb_pool_mark_dirty(amrb_pool* p)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is open");
+    p->carry_valid = false;
     return AMRB_OK;
 }
 
@@ -843,10 +900,36 @@ static amrb_status check_range(const amrb_pool* p, int field, size_t first, size
     return AMRB_OK;
 }
 
+// patches per staging chunk of the padded <-> interior-only conversions (bounded staging memory for
+// pools of millions of patches)
+static size_t stage_chunk(const amrb_pool* p)
+{
+    const size_t target = (size_t)256 << 20; // bytes
+    return std::max<size_t>(1, target / (p->pflat * sizeof(double)));
+}
+
 amrb_status amrb_pool_upload(amrb_pool* p, int field, size_t first, size_t n, const double* host)
 {
     AMRB_TRY(check_range(p, field, first, n, host));
     AMRB_TRY(set_device(p));
+    if (p->dense)
+    {
+        // host patches are padded, the pool keeps interiors only: stage chunks of padded patches and
+        // scatter their interiors (ghost values of the host image are dropped: the device gathers them)
+        const size_t chunk = stage_chunk(p);
+        for (size_t s = 0; s < n; s += chunk)
+        {
+            const size_t m = std::min(chunk, n - s);
+            AMRB_TRY(ensure_stage(p, m * p->pflat));
+            AMRB_CUDA(cudaMemcpyAsync(p->d_stage, host + s * p->pflat, m * p->pflat * sizeof(double),
+                                      cudaMemcpyHostToDevice, p->stream));
+            p->ops->interior(p->stream, p->d_stage, p->cur.p[field] + (first + s) * p->flat, (int)m, 0);
+            AMRB_TRY(check_launch(p, "interior_copy_kernel"));
+            AMRB_CUDA(cudaStreamSynchronize(p->stream));
+        }
+        p->carry_valid = false;
+        return AMRB_OK;
+    }
     AMRB_CUDA(cudaMemcpyAsync(p->cur.p[field] + first * p->flat, host, n * p->flat * sizeof(double),
                               cudaMemcpyHostToDevice, p->stream));
     AMRB_CUDA(cudaStreamSynchronize(p->stream));
@@ -857,6 +940,25 @@ amrb_status amrb_pool_download(amrb_pool* p, int field, size_t first, size_t n, 
 {
     AMRB_TRY(check_range(p, field, first, n, host));
     AMRB_TRY(set_device(p));
+    if (p->dense)
+    {
+        // padded image = interior + face ghosts gathered on the fly (what halo_kernel would have
+        // materialised), zeros in the edge / corner ghosts
+        const size_t chunk = stage_chunk(p);
+        const int    tabled = p->d_nbr ? (int)p->n_owned : 0;
+        for (size_t s = 0; s < n; s += chunk)
+        {
+            const size_t m = std::min(chunk, n - s);
+            AMRB_TRY(ensure_stage(p, m * p->pflat));
+            p->ops->export_padded(p->stream, p->cur.p[field], p->d_nbr, p->d_meta, (int)(first + s), (int)m,
+                                  tabled, p->d_stage);
+            AMRB_TRY(check_launch(p, "dense_export_kernel"));
+            AMRB_CUDA(cudaMemcpyAsync(host + s * p->pflat, p->d_stage, m * p->pflat * sizeof(double),
+                                      cudaMemcpyDeviceToHost, p->stream));
+            AMRB_CUDA(cudaStreamSynchronize(p->stream));
+        }
+        return AMRB_OK;
+    }
     AMRB_TRY(amrb_pool_ensure_halos(p));
     AMRB_CUDA(cudaMemcpyAsync(host, p->cur.p[field] + first * p->flat, n * p->flat * sizeof(double),
                               cudaMemcpyDeviceToHost, p->stream));
@@ -869,12 +971,26 @@ amrb_status amrb_pool_upload_interior(amrb_pool* p, int field, size_t first, siz
     AMRB_TRY(check_range(p, field, first, n, host));
     AMRB_TRY(set_device(p));
     if (n == 0) return AMRB_OK;
-    AMRB_TRY(ensure_stage(p, n * p->data));
-    AMRB_CUDA(cudaMemcpyAsync(p->d_stage, host, n * p->data * sizeof(double), cudaMemcpyHostToDevice,
-                              p->stream));
-    p->ops->interior(p->stream, p->cur.p[field] + first * p->flat, p->d_stage, (int)n, 1);
-    AMRB_TRY(check_launch(p, "interior_copy_kernel"));
-    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    if (p->dense)
+    {
+        // the host array already has the pool's layout: one bulk copy
+        AMRB_CUDA(cudaMemcpyAsync(p->cur.p[field] + first * p->flat, host, n * p->flat * sizeof(double),
+                                  cudaMemcpyHostToDevice, p->stream));
+        AMRB_CUDA(cudaStreamSynchronize(p->stream));
+        p->carry_valid = false;
+        return AMRB_OK;
+    }
+    const size_t chunk = stage_chunk(p);
+    for (size_t s = 0; s < n; s += chunk)
+    {
+        const size_t m = std::min(chunk, n - s);
+        AMRB_TRY(ensure_stage(p, m * p->data));
+        AMRB_CUDA(cudaMemcpyAsync(p->d_stage, host + s * p->data, m * p->data * sizeof(double),
+                                  cudaMemcpyHostToDevice, p->stream));
+        p->ops->interior(p->stream, p->cur.p[field] + (first + s) * p->flat, p->d_stage, (int)m, 1);
+        AMRB_TRY(check_launch(p, "interior_copy_kernel"));
+        AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    }
     p->carry_valid = false;
     return AMRB_OK;
 }
@@ -884,12 +1000,24 @@ amrb_status amrb_pool_download_interior(amrb_pool* p, int field, size_t first, s
     AMRB_TRY(check_range(p, field, first, n, host));
     AMRB_TRY(set_device(p));
     if (n == 0) return AMRB_OK;
-    AMRB_TRY(ensure_stage(p, n * p->data));
-    p->ops->interior(p->stream, p->cur.p[field] + first * p->flat, p->d_stage, (int)n, 0);
-    AMRB_TRY(check_launch(p, "interior_copy_kernel"));
-    AMRB_CUDA(cudaMemcpyAsync(host, p->d_stage, n * p->data * sizeof(double), cudaMemcpyDeviceToHost,
-                              p->stream));
-    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    if (p->dense)
+    {
+        AMRB_CUDA(cudaMemcpyAsync(host, p->cur.p[field] + first * p->flat, n * p->flat * sizeof(double),
+                                  cudaMemcpyDeviceToHost, p->stream));
+        AMRB_CUDA(cudaStreamSynchronize(p->stream));
+        return AMRB_OK;
+    }
+    const size_t chunk = stage_chunk(p);
+    for (size_t s = 0; s < n; s += chunk)
+    {
+        const size_t m = std::min(chunk, n - s);
+        AMRB_TRY(ensure_stage(p, m * p->data));
+        p->ops->interior(p->stream, p->cur.p[field] + (first + s) * p->flat, p->d_stage, (int)m, 0);
+        AMRB_TRY(check_launch(p, "interior_copy_kernel"));
+        AMRB_CUDA(cudaMemcpyAsync(host + s * p->data, p->d_stage, m * p->data * sizeof(double),
+                                  cudaMemcpyDeviceToHost, p->stream));
+        AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    }
     return AMRB_OK;
 }
 
@@ -899,8 +1027,9 @@ amrb_status amrb_pool_halo_exchange(amrb_pool* p)
     if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
     AMRB_TRY(need_topology(p));
     AMRB_TRY(set_device(p));
-    p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
     p->halos_stale = false;
+    if (p->dense) return AMRB_OK; // no stored ghosts: every reader gathers them from the interiors
+    p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
     return check_launch(p, "halo_kernel");
 }
 
@@ -975,6 +1104,7 @@ amrb_status amrb_pool_step(amrb_pool* p, double dt)
     AMRB_TRY(check_launch(p, "step_kernel"));
     swap_buffers(p);
     p->carry_valid = false;
+    p->halos_stale = true; // the ghosts of the new current buffer are copies / two steps old
     return AMRB_OK;
 }
 
@@ -1067,13 +1197,18 @@ amrb_status amrb_pool_batch_end(amrb_pool* p, int materialise_halos)
     if (!p) return fail(AMRB_ERR_ARGUMENT, "null pool");
     if (!p->batch_open || p->step_touched) return fail(AMRB_ERR_STATE, "batch not open or step uncommitted");
     AMRB_TRY(set_device(p));
-    if (materialise_halos)
+    if (materialise_halos && !p->dense)
     {
         // post-condition of every reference step: face halos of the current buffer are filled
         // (amr_solver.hpp:351-352)
         p->ops->halo_fill(p->stream, p->cur, p->d_nbr, p->d_meta, (int)p->n_owned);
         AMRB_TRY(check_launch(p, "halo_kernel"));
+        p->halos_stale = false;
     }
+    else if (p->dense)
+        p->halos_stale = false;
+    else
+        p->halos_stale = true;
     p->batch_steps = p->batch_k; // slot index of the dt-min of the final state
     if (p->batch_k > 0)
         AMRB_CUDA(cudaMemcpyAsync(p->h_dts, p->d_dts, p->batch_k * sizeof(double),
@@ -1101,14 +1236,19 @@ amrb_status amrb_pool_advance_batch_async(amrb_pool* p, size_t steps, double rem
     AMRB_TRY(amrb_pool_batch_begin(p, steps, remaining));
     for (size_t k = 0; k < steps; ++k)
     {
-        AMRB_TRY(amrb_pool_step_partial(p, nullptr, 0));
-        AMRB_TRY(amrb_pool_step_commit(p));
+        amrb_status s = amrb_pool_step_partial(p, nullptr, 0);
+        if (s == AMRB_OK) s = amrb_pool_step_commit(p);
+        if (s != AMRB_OK)
+        {
+            // close the batch: a failed launch must not leave the pool refusing every later call
+            p->batch_open   = false;
+            p->step_touched = false;
+            p->carry_valid  = false;
+            p->halos_stale  = true;
+            return s;
+        }
     }
-    if (p->lazy_halos && p->mode != 1)
-    {
-        p->halos_stale = true;
-        return amrb_pool_batch_end(p, 0);
-    }
+    if (p->lazy_halos && p->mode != 1) return amrb_pool_batch_end(p, 0);
     return amrb_pool_batch_end(p, 1);
 }
 
@@ -1216,8 +1356,12 @@ amrb_status amrb_pool_patch_max_flags(amrb_pool* p, int field, double refine_thr
         AMRB_CUDA(cudaMalloc(&p->d_flags, p->n_owned * 2));
         p->flags_cap = p->n_owned * 2;
     }
-    p->ops->flags(p->stream, p->cur.p[field], p->d_level, (int)p->n_owned, refine_threshold,
-                  coarsen_threshold, min_level, max_level, p->d_flags);
+    if (p->dense)
+        p->ops->flags_dense(p->stream, p->cur.p[field], p->d_nbr, p->d_meta, p->d_level, (int)p->n_owned,
+                            refine_threshold, coarsen_threshold, min_level, max_level, p->d_flags);
+    else
+        p->ops->flags(p->stream, p->cur.p[field], p->d_level, (int)p->n_owned, refine_threshold,
+                      coarsen_threshold, min_level, max_level, p->d_flags);
     AMRB_TRY(check_launch(p, "patch_max_flags_kernel"));
     AMRB_CUDA(cudaMemcpyAsync(flags, p->d_flags, p->n_owned, cudaMemcpyDeviceToHost, p->stream));
     AMRB_CUDA(cudaStreamSynchronize(p->stream));
@@ -1253,17 +1397,17 @@ amrb_status amrb_profile_capture_stop(void)
     AMRB_CUDA(cudaProfilerStop());
     return AMRB_OK;
 }
-// NVTX is not linked into this library; ranges are kept as a thread-local label stack so that the
-// reference's scoped_profile_range call sites stay valid.
-static thread_local std::vector<std::string> g_ranges;
+// NVTX v3 is header-only (the injection library is looked up at run time, a no-op without a
+// profiler attached): same range names as the reference's scoped_profile_range call sites
+// (src/cuda/device_buffer.cu:229-237).
 amrb_status amrb_profile_range_push(const char* label)
 {
-    g_ranges.emplace_back(label ? label : "");
+    nvtxRangePushA(label ? label : "");
     return AMRB_OK;
 }
 amrb_status amrb_profile_range_pop(void)
 {
-    if (!g_ranges.empty()) g_ranges.pop_back();
+    nvtxRangePop();
     return AMRB_OK;
 }
 

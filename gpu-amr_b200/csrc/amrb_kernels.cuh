@@ -32,12 +32,18 @@ struct FieldPtrs
     double* p[kMaxVar];
 };
 
-// compile-time patch geometry: cubic patches of S^R interior cells padded by H per side
-template <int R, int S, int H>
+// compile-time patch geometry: cubic patches of S^R interior cells with H ghost layers per side.
+// HS = ghost layers that are STORED: HS == H is the reference's padded device layout; HS == 0 the
+// interior-only layout of rank-3 pools (amrb_layout.storage = AMRB_STORAGE_INTERIOR), where a
+// field-patch is S^R contiguous doubles and ghosts only ever exist inside the kernels.  Multi-indices
+// are always LOGICAL padded coordinates (interior = [H, H+S)); storage offset = (i - H + HS) * pitch.
+template <int R, int S, int H, int HS = H>
 struct Geo
 {
     static constexpr int rank = R;
-    static constexpr int P    = S + 2 * H;                    // padded extent
+    static constexpr int O    = HS;                           // storage coordinate of logical index H
+    static constexpr int SH   = H - HS;                       // logical -> storage index shift
+    static constexpr int P    = S + 2 * HS;                   // stored extent per dim
     static constexpr int FLAT = (R == 2) ? P * P : P * P * P; // doubles per field-patch
     static constexpr int DATA = (R == 2) ? S * S : S * S * S;
     static constexpr int NDIR = 2 * R;
@@ -95,12 +101,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // Value of ghost cell `idx` (padded multi-index, idx[dim] in the ghost range of direction d)
 // gathered from the neighbor patch(es) across face d.   field = base pointer of one field's
 // patch array.  nb = KF neighbor indices, meta = rel | quadrant bits << 2.
-template <int R, int S, int H>
+template <int R, int S, int H, int HS = H>
 __device__ __forceinline__ double
 halo_source(const double* __restrict__ field, const int32_t* __restrict__ nb, int meta, int d,
             const int (&idx)[R])
 {
-    using G        = Geo<R, S, H>;
+    using G        = Geo<R, S, H, HS>;
     const int dim  = d >> 1;
     const int pos  = d & 1;
     const int rel  = meta & 3;
@@ -113,7 +119,7 @@ halo_source(const double* __restrict__ field, const int32_t* __restrict__ nb, in
         // same_t (patch_utils.hpp:315-332)
         int off = 0;
 #pragma unroll
-        for (int k = 0; k < R; ++k) off += from[k] * G::pitch(k);
+        for (int k = 0; k < R; ++k) off += (from[k] - G::SH) * G::pitch(k);
         return __ldg(field + (size_t)nb[0] * G::FLAT + off);
     }
     if (rel == 3)
@@ -125,7 +131,7 @@ halo_source(const double* __restrict__ field, const int32_t* __restrict__ nb, in
         for (int k = 0; k < R; ++k)
         {
             const int q = (meta >> (2 + k)) & 1;
-            off += (H + q * (S / 2) + (from[k] - H) / 2) * G::pitch(k);
+            off += (G::O + q * (S / 2) + (from[k] - H) / 2) * G::pitch(k);
         }
         return __ldg(field + (size_t)nb[0] * G::FLAT + off);
     }
@@ -137,7 +143,7 @@ halo_source(const double* __restrict__ field, const int32_t* __restrict__ nb, in
 #pragma unroll
         for (int k = 0; k < R; ++k)
         {
-            base += ((((from[k] - H) * 2) % S) + H) * G::pitch(k);
+            base += ((((from[k] - H) * 2) % S) + G::O) * G::pitch(k);
             if (k != dim)
             {
                 fine += ((idx[k] - H) / (S / 2)) * mul;
@@ -239,7 +245,7 @@ __device__ __forceinline__ int topo_find(const uint64_t* __restrict__ ids, int n
     }
     return (lo < n && ids[lo] == key) ? lo : -1;
 }
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 topology_kernel(const uint64_t* __restrict__ ids, int n, int rank, int depth, int32_t* __restrict__ level,
                 uint8_t* __restrict__ meta, int32_t* __restrict__ nbr)
 {
@@ -374,6 +380,7 @@ struct StepArgs
                                 // a warp takes its next task when it finishes one, so warps slowed
                                 // down by coarse/fine faces do not drift out of the common window;
                                 // zeroed by the host in stream order before the launch
+    int            variant;     // host side only: which instantiation the dispatcher launches
     double         gamma;
     double         dx[kMaxLevel + 1][3]; // per level, per solver direction (x,y,z)
     StepScalars    sc;
@@ -725,12 +732,12 @@ __global__ void __launch_bounds__(NT) step_kernel(const __grid_constant__ StepAr
 }
 
 // ---- standalone CFL reduction over the current buffer (first step of a batch) ----------------------
-template <int R, int S, int H, int EQ, int NT>
+template <int R, int S, int H, int EQ, int NT, int HS = H>
 __global__ void __launch_bounds__(NT)
 compute_dt_kernel(FieldPtrs cur, const int32_t* __restrict__ level, int n_patches, double gamma,
                   const __grid_constant__ StepArgs a, unsigned long long* dtmin_out)
 {
-    using G          = Geo<R, S, H>;
+    using G          = Geo<R, S, H, HS>;
     constexpr int NV = EqTraits<EQ, R>::NV;
     __shared__ double red[R * (NT / 32)];
     const int p = blockIdx.x;
@@ -746,7 +753,7 @@ compute_dt_kernel(FieldPtrs cur, const int32_t* __restrict__ level, int n_patche
 #pragma unroll
             for (int k = R - 1; k >= 0; --k)
             {
-                gl += (H + (r % S)) * G::pitch(k);
+                gl += (G::O + (r % S)) * G::pitch(k);
                 r /= S;
             }
             double U[NV];
@@ -781,7 +788,7 @@ compute_dt_kernel(FieldPtrs cur, const int32_t* __restrict__ level, int n_patche
 }
 
 // ---- batch scalar init: dtmin[1..n] = DBL_MAX, remaining[0] = remaining -----------------------------
-__global__ void init_scalars_kernel(unsigned long long* dtmin, int first, int count,
+static __global__ void init_scalars_kernel(unsigned long long* dtmin, int first, int count,
                                     double* remaining, double remaining_value, double* dts)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -798,12 +805,12 @@ __global__ void init_scalars_kernel(unsigned long long* dtmin, int first, int co
 //               kind 1: prolongation of child `child` from old patch src (ndtree.hpp:1528-1555)
 //               kind 2: restriction of old patches src .. src+2^R-1       (ndtree.hpp:1499-1526)
 // child number c: row-major over (2,..,2), last layout dim = bit 0 (ndtree.hpp:1463-1497)
-template <int R, int S, int H, int NV>
+template <int R, int S, int H, int NV, int HS = H>
 __global__ void __launch_bounds__(256)
 plan_kernel(FieldPtrs old_, FieldPtrs new_, const int8_t* __restrict__ kind,
             const int32_t* __restrict__ src, const int8_t* __restrict__ child, int n_new)
 {
-    using G     = Geo<R, S, H>;
+    using G     = Geo<R, S, H, HS>;
     const int q = blockIdx.x;
     if (q >= n_new) return;
     const int    kd = kind[q];
@@ -819,10 +826,13 @@ plan_kernel(FieldPtrs old_, FieldPtrs new_, const int8_t* __restrict__ kind,
         return;
     }
     // ghosts of freshly created patches are zero until the next halo exchange
-    for (int f = 0; f < NV; ++f)
-        for (int i = threadIdx.x; i < G::FLAT; i += blockDim.x)
-            new_.p[f][(size_t)q * G::FLAT + i] = 0.0;
-    __syncthreads();
+    if constexpr (HS > 0)
+    {
+        for (int f = 0; f < NV; ++f)
+            for (int i = threadIdx.x; i < G::FLAT; i += blockDim.x)
+                new_.p[f][(size_t)q * G::FLAT + i] = 0.0;
+        __syncthreads();
+    }
     const int cn = child[q];
     for (int ci = threadIdx.x; ci < G::DATA; ci += blockDim.x)
     {
@@ -832,7 +842,7 @@ plan_kernel(FieldPtrs old_, FieldPtrs new_, const int8_t* __restrict__ kind,
         {
             i[k] = r % S;
             r /= S;
-            gl += (H + i[k]) * G::pitch(k);
+            gl += (G::O + i[k]) * G::pitch(k);
         }
         if (kd == 1)
         {
@@ -842,7 +852,7 @@ plan_kernel(FieldPtrs old_, FieldPtrs new_, const int8_t* __restrict__ kind,
             for (int k = 0; k < R; ++k)
             {
                 const int cb = (cn >> (R - 1 - k)) & 1;
-                co += (H + cb * (S / 2) + i[k] / 2) * G::pitch(k);
+                co += (G::O + cb * (S / 2) + i[k] / 2) * G::pitch(k);
             }
             for (int f = 0; f < NV; ++f)
                 new_.p[f][(size_t)q * G::FLAT + gl] = old_.p[f][s0 * G::FLAT + co];
@@ -855,7 +865,7 @@ plan_kernel(FieldPtrs old_, FieldPtrs new_, const int8_t* __restrict__ kind,
             for (int k = 0; k < R; ++k)
             {
                 ch |= (i[k] / (S / 2)) << (R - 1 - k);
-                base += (H + (i[k] % (S / 2)) * 2) * G::pitch(k);
+                base += (G::O + (i[k] % (S / 2)) * 2) * G::pitch(k);
             }
             for (int f = 0; f < NV; ++f)
             {
@@ -913,7 +923,7 @@ patch_max_flags_kernel(const double* __restrict__ field, const int32_t* __restri
 }
 
 // runtime-sized variant behind the raw-pointer criterion entry point
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 patch_max_flags_rt_kernel(const double* __restrict__ field, const int32_t* __restrict__ level,
                           int n_patches, int flat, double refine_thr, double coarsen_thr,
                           int min_level, int max_level, int8_t* __restrict__ flags)
@@ -984,12 +994,12 @@ struct SlabGeo
     static constexpr int SLAB = T * Geo<R, S, H>::FACE;
 };
 
-template <int R, int S, int H, int NV>
+template <int R, int S, int H, int NV, int HS = H>
 __global__ void __launch_bounds__(128)
 face_pack_kernel(FieldPtrs cur, const int32_t* __restrict__ entries, int count,
                  double* __restrict__ buffer, int unpack)
 {
-    using G     = Geo<R, S, H>;
+    using G     = Geo<R, S, H, HS>;
     const int e = blockIdx.x;
     if (e >= count) return;
     const int     p = entries[2 * e], d = entries[2 * e + 1];
@@ -1004,10 +1014,10 @@ face_pack_kernel(FieldPtrs cur, const int32_t* __restrict__ entries, int count,
         {
             int i;
             if (k == dim)
-                i = pos ? (H + S - 1 - layer) : (H + layer);
+                i = pos ? (G::O + S - 1 - layer) : (G::O + layer);
             else
             {
-                i = H + (t % S);
+                i = G::O + (t % S);
                 t /= S;
             }
             gl += i * G::pitch(k);

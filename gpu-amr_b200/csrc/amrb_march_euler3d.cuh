@@ -127,7 +127,7 @@ __device__ __forceinline__ void flux3_xy(const Cell3& L, const Cell3& R, int ds,
 // last-dim-fastest like hypercube_offset (patch_utils.hpp:203-234, intergrid_operator.hpp:92-106).
 // Kept out of line: coarse/fine faces are a small minority of all faces and the marching loop has
 // to stay inside the instruction cache.
-__device__ __noinline__ void fine_mean5(const FieldPtrs& cur, size_t o, int P, int PP, double* out)
+static __device__ __noinline__ void fine_mean5(const FieldPtrs& cur, size_t o, int P, int PP, double* out)
 {
 #pragma unroll 1
     for (int f = 0; f < 5; ++f)

@@ -173,6 +173,7 @@ class ShardedSolver:
             self.ar_group = dist.new_group(ranks=list(range(world)))
         self.graphs = {}
         self._dtmin_cache = {}
+        self._dtmin_base = 0
         self.launches = 0
         self._install_exchange()
 
@@ -209,6 +210,9 @@ class ShardedSolver:
         kind, src, child = plan
         old_bounds = [(r * old_size) // self.world for r in range(self.world + 1)]
         rp = ReshardPlan(old_bounds, new_host_tree.size, kind, src, child, 1 << self.cfg.rank, self.world)
+        if rp.staging_slots(self.rank) > self.capacity:   # before phase A writes into the next buffer
+            raise B.AmrbError("re-slicing needs %d staging slots, pool capacity is %d"
+                              % (rp.staging_slots(self.rank), self.capacity))
         self.halo_exchange()                    # copied patches carry their halos along
         self.torch.cuda.synchronize()
         migrate_old_patches(rp, self.rank, self.pool.flat, self.field_views("cur"),
@@ -279,10 +283,21 @@ class ShardedSolver:
 
     # ---- stepping
     def _dtmin_tensor(self, k):
-        t = self._dtmin_cache.get(k)
+        """torch view of the dt-min slot entering step k.  The library re-allocates its scalar arrays when
+        a batch needs more slots than any batch before (amrb_pool_batch_begin), so the views are keyed by
+        the slot's CURRENT device address, never by k alone; recorded graphs hold the old addresses and
+        are dropped with them."""
+        ptr = int(self.L.amrb_pool_dtmin_slot(self.pool.h, k) or 0)
+        if ptr == 0:
+            raise B.AmrbError("no dt-min slot %d in the open batch" % k)
+        if k == 0 and ptr != self._dtmin_base:
+            self._dtmin_base = ptr
+            self._dtmin_cache = {}
+            self.graphs = {}
+        t = self._dtmin_cache.get(ptr)
         if t is None:
-            t = raw_tensor(self.L.amrb_pool_dtmin_slot(self.pool.h, k), 1, self.torch)
-            self._dtmin_cache[k] = t
+            t = raw_tensor(ptr, 1, self.torch)
+            self._dtmin_cache[ptr] = t
         return t
 
     def _allreduce_dtmin(self, k):
@@ -300,7 +315,6 @@ class ShardedSolver:
     def advance_batch_async(self, steps, remaining=B.DBL_MAX, overlap=True):
         L, h, pl = self.L, self.pool.h, self.plan
         B.check(L.amrb_pool_batch_begin(h, steps, remaining))
-        self._dtmin_cache = {} if len(self._dtmin_cache) > 4096 else self._dtmin_cache
         self._allreduce_dtmin(0)
         for k in range(steps):
             self._pack()

@@ -127,6 +127,54 @@ def c2_config():
     return Config(2, 64, 1, 7, B.EQ_EULER)
 
 
+# BASELINE config C3 (benchmark/bench_fvm_solver_integration3D.b.cpp:31-64 patch shape: 8^3 Euler, halo 1)
+# as the static multi-level tree of ~1e9 cells SURVEY 8d names: uniform level 6 (262 144 patches), every
+# leaf within 0.42 L of the centre refined to level 7, every leaf within 0.27 L to level 8
+# (2:1-balanced by construction) -> ~2.1e6 patches, ~1.07e9 cells, levels 6-8, morton_id<8,3>.
+# base_level < 6 gives the geometrically similar mesh with 8x fewer cells per level dropped (the
+# bounded samples of the CPU / reference-CUDA baseline legs).
+C3 = dict(base_level=6, ball_radii=(0.42, 0.27), depth=8, patches=2037232, cells=1043062784)
+
+
+def c3_config():
+    return Config(3, 8, 1, C3["depth"], B.EQ_EULER)
+
+
+def c3_script(base_level=6):
+    d = C3["depth"]
+    return "\n".join(["A\nX"] * base_level + ["B %g 99 %d 0.5 0.5 0.5" % (C3["ball_radii"][0], d), "X",
+                                              "B %g 99 %d 0.5 0.5 0.5" % (C3["ball_radii"][1], d), "X"])
+
+
+def device_initial_condition(torch, ids, cfg, device, chunk=32768):
+    """The same cell-centre initial conditions evaluated ON THE DEVICE (torch elementwise ops), for meshes
+    whose host image would not fit a benchmark's time or memory budget (1e9 cells): yields
+    (first_patch, [nvar] tensors of shape [n, S..]) per chunk of patches.  Synthetic-input plumbing only."""
+    R, S, L = cfg.rank, cfg.size, cfg.length
+    coords, lvl = morton_decode(ids, R)
+    span = float(1 << cfg.depth)
+    k = (torch.arange(S, dtype=torch.float64, device=device) + 0.5)
+    c0 = 0.5 * L if cfg.eq == B.EQ_EULER else 0.2 * L
+    for s in range(0, len(ids), chunk):
+        n = min(chunk, len(ids) - s)
+        ext = torch.from_numpy((2.0 ** (cfg.depth - lvl[s:s + n])) / span).to(device)
+        r2 = torch.zeros((n,) + (S,) * R, dtype=torch.float64, device=device)
+        for d in range(R):                       # physical axis d <-> layout dim R-1-d
+            org = torch.from_numpy(coords[s:s + n, d].astype(np.float64) / span * L).to(device)
+            dx = ext * L / S
+            shape = [n] + [1] * R
+            kshape = [1] * (R + 1)
+            kshape[1 + (R - 1 - d)] = S
+            x = org.reshape(shape) + k.reshape(kshape) * dx.reshape(shape)
+            r2 = r2 + (x - c0) ** 2
+        if cfg.eq == B.EQ_EULER:
+            g = torch.exp(-r2 / (0.01 * L * L))
+            z = torch.zeros_like(g)
+            yield s, [0.5 + 2.0 * g] + [z] * R + [(1.0 + 10.0 * g) / (cfg.gamma - 1.0)]
+        else:
+            yield s, [torch.exp(-r2 / (0.005 * L * L))]
+
+
 def c2_script(base_level=5):
     """the same mesh in the oracle/ref_dump script language (for the CPU baseline legs);
     base_level < 5 gives the geometrically similar mesh with 4x fewer cells per level dropped"""

@@ -41,6 +41,14 @@ enum { AMRB_EQ_ADVECTION = 0, AMRB_EQ_EULER = 1 };             /* solver/{Advect
 enum { AMRB_REL_NONE = 0, AMRB_REL_SAME = 1, AMRB_REL_FINER = 2, AMRB_REL_COARSER = 3 };
                                                                 /* cuda/halo_exchange.hpp:11-17 */
 enum { AMRB_STABLE = 0, AMRB_REFINE = 1, AMRB_COARSEN = 2 };   /* ndtree.hpp:265-270 refine_status_t */
+/* device storage of a field-patch:
+ *   PADDED   the reference's device layout (ndtree.hpp:341-362): prod(size + 2*halo) doubles, ghosts stored;
+ *   INTERIOR prod(size) doubles, no ghosts anywhere in HBM: the fused step gathers its ghost layer from the
+ *            neighbor interiors anyway, so storing ghosts only costs traffic and memory (3D 8^3 patches:
+ *            6 400 + 6 400 B moved per 4 096 algorithmic; 1.07e9 cells: 168 GB instead of 86 GB).  Rank 3,
+ *            halo 1, sizes 8 and 16.  The host exchange format (amrb_pool_upload / download, VTK output)
+ *            stays the padded patch; the padded image is built in a staging buffer on demand. */
+enum { AMRB_STORAGE_PADDED = 0, AMRB_STORAGE_INTERIOR = 1 };
 
 const char* amrb_last_error(void);
 const char* amrb_version(void);
@@ -81,12 +89,14 @@ typedef struct amrb_layout
     int32_t nvar;      /* fields per cell: 1 (advection) or rank+2 (Euler) */
     int32_t equation;  /* AMRB_EQ_* */
     int32_t depth;     /* morton_id<Depth,Rank>: finest level */
+    int32_t storage;   /* AMRB_STORAGE_* */
 } amrb_layout;
 
 /* 1 if fused kernels for this shape were compiled into the library */
 int    amrb_layout_supported(const amrb_layout* layout);
-size_t amrb_layout_flat_size(const amrb_layout* layout); /* prod(size+2*halo) */
+size_t amrb_layout_flat_size(const amrb_layout* layout); /* prod(size+2*halo): the padded (host) patch */
 size_t amrb_layout_data_size(const amrb_layout* layout); /* prod(size)        */
+size_t amrb_layout_storage_size(const amrb_layout* layout); /* doubles per field-patch in the pool */
 
 /* ------------------------------------------------------------------------------------------
  * 3. device patch pool — replaces ndtree's m_data_buffers / m_next_buffers device mirrors,
@@ -107,7 +117,8 @@ amrb_status amrb_pool_destroy(amrb_pool* pool);
 size_t      amrb_pool_capacity(const amrb_pool* pool);
 size_t      amrb_pool_size(const amrb_pool* pool);
 void*       amrb_pool_stream(const amrb_pool* pool);
-/* current-buffer device pointer of field f (ndtree::get_device_buffer, ndtree.hpp:561-581) */
+/* current-buffer device pointer of field f (ndtree::get_device_buffer, ndtree.hpp:561-581); patch p
+ * starts at p * amrb_layout_storage_size(layout) doubles */
 double*     amrb_pool_field(const amrb_pool* pool, int field);
 double*     amrb_pool_next_field(const amrb_pool* pool, int field);
 /* current <-> next (ndtree::swap_buffers, ndtree.hpp:1558-1579) for callers that filled the next buffer
@@ -190,6 +201,16 @@ uint64_t amrb_pool_launch_count(const amrb_pool* pool);
  * 1 = unfused (materialise halos every step, then the same stencil kernel without gather),
  * 2 = first-generation fused kernel (thread per cell) — 1 and 2 are kept for A/B measurement */
 amrb_status amrb_pool_set_mode(amrb_pool* pool, int mode);
+/* kernel variant inside mode 0, for A/B measurement and variant-agreement tests (0 = default; the values
+ * are listed next to the dispatch in csrc/amrb_api.cu; initial value = environment AMRB_VARIANT) */
+amrb_status amrb_pool_set_variant(amrb_pool* pool, int variant);
+/* The carried CFL minimum: a batch ends with the dt-min of its final state, and the next batch starts
+ * from it without a compute_dt pass.  Every entry point of this library that changes the state
+ * (upload, apply_plan, set_topology, swap_buffers, set_physics) drops it.  A caller that writes the
+ * current buffer through amrb_pool_field / amrb_pool_next_field pointers (get_device_buffer) MUST call
+ * amrb_pool_mark_dirty afterwards, otherwise the next batch takes its first step with the dt of the
+ * overwritten state. */
+amrb_status amrb_pool_mark_dirty(amrb_pool* pool);
 
 /* the same batch, decomposed so that a multi-GPU driver can interleave ghost-face traffic:
  *   batch_begin(max_steps, remaining)

@@ -17,7 +17,9 @@
 #include <array>
 #include <cstddef>
 #include <limits>
+#include <stdexcept>
 #include <tuple>
+#include <type_traits>
 #include <utility>
 
 template <typename TreeT, typename GeometryT, typename EquationT, int DIM>
@@ -33,9 +35,20 @@ public:
     static constexpr int NVAR = EquationT::NVAR;
     static_assert(static_cast<std::size_t>(NVAR) == TreeT::s_nvar, "equation and cell payload disagree");
     static_assert(static_cast<std::size_t>(DIM) == TreeT::s_rank, "DIM must equal the tree rank");
+    // the device kernels implement exactly these two equation policies (the reference instantiates its
+    // GPU kernels for the same set, src/cuda/fvm_time_step.cu:286-332); any other policy with 1 or
+    // DIM+2 fields must not silently run the built-in physics
+    static constexpr bool s_is_advection = std::is_same_v<EquationT, AdvectionPhysics<DIM>>;
+    static constexpr bool s_is_euler     = std::is_same_v<EquationT, EulerPhysics<DIM>>;
+    static_assert(s_is_advection || s_is_euler,
+                  "the device path implements AdvectionPhysics<DIM> and EulerPhysics<DIM> only (no CPU fallback)");
 
-    amr_solver(std::size_t capacity, double gamma, double cfl) : m_tree(capacity), m_gamma(gamma), m_cfl(cfl)
+    // same defaults as the reference constructor (amr_solver.hpp:62-69)
+    amr_solver(std::size_t capacity, double gamma = 1.4, double cfl = 0.1)
+        : m_tree(capacity), m_gamma(gamma), m_cfl(cfl)
     {
+        if (m_tree.layout().equation != (s_is_advection ? AMRB_EQ_ADVECTION : AMRB_EQ_EULER))
+            throw std::logic_error("amr_solver: the tree's cell payload does not match the equation policy");
         const auto len = GeometryT::lengths();
         double     L[3] = { 1.0, 1.0, 1.0 };
         for (int i = 0; i < DIM; ++i) L[i] = len[static_cast<std::size_t>(i)];
@@ -44,6 +57,8 @@ public:
 
     [[nodiscard]] auto get_tree() noexcept -> TreeT& { return m_tree; }
     [[nodiscard]] auto get_tree() const noexcept -> TreeT const& { return m_tree; }
+    [[nodiscard]] auto get_gamma() const noexcept -> double { return m_gamma; }
+    [[nodiscard]] auto get_cfl() const noexcept -> double { return m_cfl; }
 
     // ic(cell-centre coordinates) -> primitive state; stored as conservative variables in the
     // interior of every patch (amr_solver.hpp:105-145 of the reference).  Evaluated on the host

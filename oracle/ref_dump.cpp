@@ -35,6 +35,13 @@
 //   T n                    time n x advance() and print one JSON line (updates/s)
 //   V name                 vtk_print(tree) -> vtk_output/<name>.vtk in the working directory
 //   D tag                  dump ids, neighbor tables, padded data, under "tag/"
+//
+// With -DAMR_ENABLE_CUDA_AMR=1 (oracle/Makefile target _ref/ref_cuda_bench_*: this file + the
+// reference's own src/cuda/*.cu compiled for sm_100) the same script drives the reference's CUDA
+// backend, with the sync calls the reference's benchmark makes
+// (benchmark/bench_fvm_solver_integration.b.cpp:181-197): before I the mirror is pushed / pulled
+// around every halo exchange, from I on the state lives on the device and D pulls it back.  That is
+// the GPU-vs-GPU baseline of SURVEY 8d ("the kernel to beat on the same box").
 // Output (argv[2]): flat sequence of records
 //   u32 name_len | name | u32 dtype(0=f64,1=i64,2=i32,3=i8,4=u64) | u32 ndim | u64 shape[ndim] | raw data
 
@@ -317,6 +324,9 @@ int main(int argc, char** argv)
     std::ifstream       script(argv[1]);
     std::string         line;
     std::vector<double> dts;
+#ifdef AMR_ENABLE_CUDA_AMR
+    bool device_live = false; // the device holds the authoritative state (after I)
+#endif
     while (std::getline(script, line))
     {
         std::istringstream is(line);
@@ -385,7 +395,16 @@ int main(int argc, char** argv)
         }
         else if (op == "X")
         {
-            tree.halo_exchange_update();
+#ifdef AMR_ENABLE_CUDA_AMR
+            if (!device_live)
+            {
+                tree.sync_current_to_device();
+                tree.halo_exchange_update();
+                tree.sync_current_from_device();
+            }
+            else
+#endif
+                tree.halo_exchange_update();
         }
         else if (op == "P")
         {
@@ -394,6 +413,11 @@ int main(int argc, char** argv)
         else if (op == "I")
         {
             solver.initialize(ic);
+#ifdef AMR_ENABLE_CUDA_AMR
+            tree.sync_current_to_device();
+            tree.build_patch_levels_on_device();
+            device_live = true;
+#endif
         }
         else if (op == "S")
         {
@@ -411,11 +435,23 @@ int main(int argc, char** argv)
             const auto        t0      = std::chrono::steady_clock::now();
             std::size_t       done    = 0;
             double            sum_dt  = 0;
+#ifdef AMR_ENABLE_CUDA_AMR
+            {
+                // one batch of n steps, as the reference's benchmark loop issues them
+                // (b.cpp:218-247); finish_advance_batch waits for the fence recorded after the
+                // batch's last launch on the default stream
+                std::size_t executed = 0;
+                solver.advance_batch_async(static_cast<std::size_t>(n));
+                sum_dt += solver.finish_advance_batch(&executed);
+                done = executed;
+            }
+#else
             for (int i = 0; i != n; ++i)
             {
                 sum_dt += solver.advance();
                 ++done;
             }
+#endif
             const std::chrono::duration<double> el = std::chrono::steady_clock::now() - t0;
             const double updates = static_cast<double>(done) * static_cast<double>(patches) *
                                    static_cast<double>(patch_layout_t::data_layout_t::flat_size());
@@ -439,6 +475,9 @@ int main(int argc, char** argv)
         {
             std::string tag;
             is >> tag;
+#ifdef AMR_ENABLE_CUDA_AMR
+            if (device_live) tree.sync_current_from_device();
+#endif
             dump(w, tag, tree);
             w.rec(tag + "/dts", 0, { dts.size() }, dts.data(), 8 * dts.size());
         }

@@ -24,6 +24,18 @@ def test_layout_queries(amrb):
     assert L.amrb_layout_supported(C.byref(lay)) == 1
     odd = amrb.make_layout(2, 12, 1, amrb.EQ_EULER, 7)
     assert L.amrb_layout_supported(C.byref(odd)) == 0
+    # interior-only device storage: rank 3, halo 1, 8^3 and 16^3 patches, both equations
+    for size in (8, 16):
+        for eq in (amrb.EQ_EULER, amrb.EQ_ADVECTION):
+            d = amrb.make_layout(3, size, 1, eq, 8, amrb.STORAGE_INTERIOR)
+            assert L.amrb_layout_supported(C.byref(d)) == 1
+            assert L.amrb_layout_storage_size(C.byref(d)) == size ** 3
+            assert L.amrb_layout_flat_size(C.byref(d)) == (size + 2) ** 3
+    assert L.amrb_layout_storage_size(C.byref(lay)) == 1000
+    for bad in (amrb.make_layout(2, 64, 1, amrb.EQ_EULER, 7, amrb.STORAGE_INTERIOR),
+                amrb.make_layout(3, 4, 1, amrb.EQ_EULER, 5, amrb.STORAGE_INTERIOR),
+                amrb.make_layout(3, 8, 1, amrb.EQ_EULER, 5, 7)):
+        assert L.amrb_layout_supported(C.byref(bad)) == 0
 
 
 def test_morton_roundtrip(amrb):

@@ -16,16 +16,26 @@ def _run(args, env=None, timeout=600):
                           text=True, timeout=timeout, cwd=ROOT, env=e)
 
 
-def test_reference_arm_prints_the_contract_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+import pytest
+
+
+@pytest.mark.parametrize("workload", ["c3", "c2"])
+def test_reference_arm_prints_the_contract_line(workload):
+    # --steps 50 selects the smallest bounded sample of the C3 family (2.1e6 cells): seconds, not minutes
+    steps = 50 if workload == "c3" else 1
+    r = _run(["--impl", "reference", "--steps", str(steps), "--warmup", "0", "--workload", workload])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cell_updates_per_sec" and d["unit"] == "cell-updates/s"
-    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == steps
     assert d["value"] > 1e6 and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["config"]["workload"].startswith("C2") and d["config"]["cells"] == 9306112
+    if workload == "c2":
+        assert d["config"]["workload"].startswith("C2") and d["config"]["cells"] == 9306112 and d["scaling"] == "weak"
+    else:
+        assert d["config"]["workload"].startswith("C3") and d["scaling"] == "strong"
+        assert d["config"]["cells"] == 1043062784 and d["config"]["sample_cells"] >= 1e6
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -29,11 +29,21 @@ def _is_probe_tag(script, tag):
     return False
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["fused", "unfused", "fused_v1"])
+def _dense_ok(cfg):
+    """shapes the interior-only device layout is instantiated for (include/gpuamr_b200.h)"""
+    return cfg.rank == 3 and cfg.halo == 1 and cfg.size in (8, 16)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, "interior"], ids=["fused", "unfused", "fused_v1", "interior_storage"])
 @pytest.mark.parametrize("name", fixtures())
 def test_device_matches_reference_dump(amrb, name, mode):
     cfg, script, g = load(name)
-    tree = amrb.DeviceTree(cfg, capacity=4096, mode=mode)
+    if mode == "interior":
+        if not _dense_ok(cfg):
+            pytest.skip("interior-only storage: rank 3, halo 1, 8^3 / 16^3 patches")
+        tree = amrb.DeviceTree(cfg, capacity=4096, mode=0, storage=amrb.STORAGE_INTERIOR)
+    else:
+        tree = amrb.DeviceTree(cfg, capacity=4096, mode=mode)
     out = O.run_script(tree, script, ic_override=ic_from_golden(cfg, script, g))
     mask = O.face_halo_mask(cfg).ravel()
     for tag in tags_in_order(script):
@@ -60,19 +70,22 @@ def test_device_matches_reference_dump(amrb, name, mode):
             np.testing.assert_allclose(full[..., mask].max(axis=(1, 2)), g[tag + "/max"], rtol=TOL)
 
 
+@pytest.mark.parametrize("storage", [0, 1], ids=["padded", "interior"])
 @pytest.mark.parametrize("cfgname,levels", [("r2_s64_h1_d7_euler", 2), ("r2_s32_h1_d7_adv", 2),
                                             ("r3_s16_h1_d5_euler", 1), ("r3_s8_h1_d5_euler", 2),
-                                            ("r3_s8_h1_d5_adv", 2),
+                                            ("r3_s8_h1_d5_adv", 2), ("r3_s16_h1_d5_adv", 1),
                                             ("r2_s10_h2_d7_euler", 2)])
-def test_device_matches_oracle_on_bench_shapes(amrb, cfgname, levels):
+def test_device_matches_oracle_on_bench_shapes(amrb, cfgname, levels, storage):
     """Shapes without a committed reference dump (the 64x64 / 16^3 benchmark patches): compare with
     the pinned C oracle on the same scripted tree, IC and step count."""
     cfg = O.Config.from_name(cfgname)
     script = "\n".join(["A\nX"] * levels + ["H 7 300 0 1 %d" % (levels + 1), "X",
                                             "H 8 250 300 1 %d" % (levels + 2), "X",
                                             "P", "X", "D probe", "I", "X", "D t0", "S 6", "D t6"])
+    if storage and not _dense_ok(cfg):
+        pytest.skip("interior-only storage: rank 3, halo 1, 8^3 / 16^3 patches")
     orc = O.OracleTree(cfg, capacity=4096)
-    dev = amrb.DeviceTree(cfg, capacity=4096)
+    dev = amrb.DeviceTree(cfg, capacity=4096, storage=storage)
     a, b = O.run_script(orc, script), O.run_script(dev, script)
     mask = O.face_halo_mask(cfg).ravel()
     for tag in ("probe", "t0", "t6"):

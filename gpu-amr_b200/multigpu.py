@@ -148,13 +148,14 @@ def raw_tensor(ptr, n, torch, dtype="<f8"):
 class ShardedSolver:
     """One rank's share of the mesh on one GPU."""
 
-    def __init__(self, cfg, host_tree, rank, world, device, dist, torch, capacity=None):
+    def __init__(self, cfg, host_tree, rank, world, device, dist, torch, capacity=None,
+                 storage=B.STORAGE_PADDED):
         self.cfg, self.rank, self.world, self.dist, self.torch = cfg, rank, world, dist, torch
         self.device = device
         levels, rel, nbr, quad = host_tree.tables()
         self.plan = pl = ShardPlan(levels, rel, nbr, quad, rank, world)
         self.ids = host_tree.ids()[pl.lo:pl.hi]
-        self.lay = B.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth)
+        self.lay = B.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage)
         # capacity: slots for owned + ghost patches; meshes that change need headroom
         self.capacity = max(pl.n_total, 1) if capacity is None else int(capacity)
         self.pool = B.DevicePool(self.lay, self.capacity, device)
@@ -199,7 +200,7 @@ class ShardedSolver:
     def field_views(self, which):
         """torch views of the whole current ('cur') / next ('nxt') field arrays of the pool"""
         get = self.L.amrb_pool_field if which == "cur" else self.L.amrb_pool_next_field
-        n = self.capacity * self.pool.flat
+        n = self.capacity * self.pool.stored
         return [raw_tensor(get(self.pool.h, f), n, self.torch) for f in range(self.cfg.nvar)]
 
     def reshard(self, new_host_tree, old_size, plan):
@@ -215,7 +216,7 @@ class ShardedSolver:
                               % (rp.staging_slots(self.rank), self.capacity))
         self.halo_exchange()                    # copied patches carry their halos along
         self.torch.cuda.synchronize()
-        migrate_old_patches(rp, self.rank, self.pool.flat, self.field_views("cur"),
+        migrate_old_patches(rp, self.rank, self.pool.stored, self.field_views("cur"),
                             self.field_views("nxt"), self.dist)
         self.torch.cuda.synchronize()
         self.finish_reshard(rp, new_host_tree)
@@ -376,9 +377,10 @@ class LocalCluster:
     copies.  Test vehicle for the sharding logic on a single-GPU box (the NCCL transport itself is
     covered by tests/test_multigpu_gpu.py on >= 2 GPUs)."""
 
-    def __init__(self, cfg, host_tree, world, device, torch, capacity=None):
+    def __init__(self, cfg, host_tree, world, device, torch, capacity=None, storage=B.STORAGE_PADDED):
         self.torch, self.world, self.cfg = torch, world, cfg
-        self.sols = [ShardedSolver(cfg, host_tree, r, world, device, None, torch, capacity=capacity)
+        self.sols = [ShardedSolver(cfg, host_tree, r, world, device, None, torch, capacity=capacity,
+                                   storage=storage)
                      for r in range(world)]
         self._index_exchange()
 
@@ -460,7 +462,7 @@ class LocalCluster:
         device-to-device copies; the NCCL form sends the same contiguous ranges), then every shard
         applies its slice of the plan and installs its new tables (phase B)"""
         kind, src, child = plan
-        flat = self.sols[0].pool.flat
+        flat = self.sols[0].pool.stored
         old_bounds = [s.plan.lo for s in self.sols] + [old_size]
         rp = ReshardPlan(old_bounds, host_tree.size, kind, src, child, 1 << self.cfg.rank, self.world)
         self.halo_exchange()                    # copied patches carry their halos along
@@ -512,7 +514,65 @@ def weak_scaled_tree(wl, world):
     return cfg, best[1], base, best[0]
 
 
+def state_checksums(torch, views, bounds, stored):
+    """order-independent integer checksums of the bit patterns of each field over each patch range
+    [bounds[r], bounds[r+1]): int64 sums with wrap-around; bit-identical states <-> identical sums"""
+    out = torch.zeros((len(views), len(bounds) - 1), dtype=torch.int64, device=views[0].device)
+    for f, v in enumerate(views):
+        iv = v.view(torch.int64)
+        for r in range(len(bounds) - 1):
+            out[f, r] = iv[int(bounds[r]) * stored:int(bounds[r + 1]) * stored].sum()
+    return out
+
+
+def check_parity(torch, dist, bench_mod, amrb, wl, cfg, host, sol, rank, world, local, storage, steps=3):
+    """Correctness evidence carried by the bench line itself: the sharded run (pack / exchange / unpack,
+    interior + boundary launches, all-reduced CFL minimum) against ONE pool holding the whole mesh on rank 0,
+    same initial condition, `steps` steps: dt sequence equal, state bit-identical (integer checksums of the
+    bit patterns per field and per rank's Morton range)."""
+    ids_all = host.ids()
+    P, stored = len(ids_all), sol.pool.stored
+    bench_mod.fill_ic(torch, amrb, wl, sol.pool, sol.ids, cfg, local)
+    sol.halo_exchange()
+    sol.advance_batch_async(steps)
+    _, n_s, dts_s = sol.finish_advance_batch(steps)
+    torch.cuda.synchronize()
+    own = [v[:sol.plan.n_owned * stored] for v in sol.field_views("cur")]
+    mine = state_checksums(torch, own, [0, sol.plan.n_owned], stored)[:, 0].contiguous()
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    ok, detail = True, {}
+    if rank == 0:
+        lay = B.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage)
+        pool = B.DevicePool(lay, P, local)
+        pool.set_physics([cfg.length] * 3, cfg.gamma, cfg.cfl)
+        pool.set_topology_from_ids(ids_all)
+        bench_mod.fill_ic(torch, amrb, wl, pool, ids_all, cfg, local)
+        pool.halo_exchange()
+        pool.advance_batch_async(steps)
+        _, n_1, dts_1 = pool.finish_advance_batch(steps)
+        torch.cuda.synchronize()
+        views = bench_mod.pool_field_views(torch, amrb, pool, P * stored, cfg.nvar)
+        ref = state_checksums(torch, views, sol.plan.bounds, stored).cpu().numpy()      # [field, rank]
+        got = torch.stack(gathered, dim=1).cpu().numpy()
+        state_ok = bool((ref == got).all())
+        dt_ok = bool(n_1 == n_s and np.array_equal(np.asarray(dts_1), np.asarray(dts_s)))
+        ok = state_ok and dt_ok
+        detail = {"checked": True, "steps": int(steps), "against": "one pool holding the whole mesh on rank 0",
+                  "state_bit_identical": state_ok, "dt_sequence_identical": dt_ok,
+                  "mismatching_field_rank_pairs": int((ref != got).sum())}
+        pool.close()
+        del views
+        torch.cuda.empty_cache()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return bool(int(flag.item())), detail
+
+
 def run_bench(args, METRIC, UNIT):
+    """N > 1.  Default: STRONG scaling of the C3 mesh (the same ~1.04e9-cell 3D tree at every N, one Morton
+    range per GPU, interior-only pools).  --workload c2: the weak-scaled C2 family of round 1."""
+    import importlib
     import json
     import sys
 
@@ -529,12 +589,29 @@ def run_bench(args, METRIC, UNIT):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
     import bench as bench_mod
+    amrb = importlib.import_module("gpu-amr_b200")
 
-    cfg, host, base, radius = weak_scaled_tree(wl, world)
-    sol = ShardedSolver(cfg, host, rank, world, local, dist, torch)
+    strong = args.workload != "c2"
+    if strong:
+        cfg = wl.c3_config()
+        base = wl.C3["base_level"] if args.workload == "c3" else int(args.workload.split("L")[-1])
+        host = wl.build_static_tree(cfg, base, wl.C3["ball_radii"])
+        storage, radius = B.STORAGE_INTERIOR, None
+    else:
+        cfg, host, base, radius = weak_scaled_tree(wl, world)
+        storage = B.STORAGE_PADDED
+    sol = ShardedSolver(cfg, host, rank, world, local, dist, torch, storage=storage)
     P = host.size
     cells = P * cfg.data
-    sol.upload_interior(wl.initial_condition(sol.ids, cfg))
+    parity_ok, parity = check_parity(torch, dist, bench_mod, amrb, wl, cfg, host, sol, rank, world, local, storage)
+    if not parity_ok:
+        if rank == 0:
+            sys.stderr.write("PARITY FAILURE (sharded vs single pool): %s\n" % json.dumps(parity))
+        dist.barrier()
+        sol.pool.close()
+        dist.destroy_process_group()
+        raise SystemExit(3)
+    bench_mod.fill_ic(torch, amrb, wl, sol.pool, sol.ids, cfg, local)
     sol.halo_exchange()
     K, W = args.steps, max(args.warmup, 3)
     sol.advance_batch_async(W)
@@ -552,7 +629,7 @@ def run_bench(args, METRIC, UNIT):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(sol.stream)
-            sol.advance_batch_async(10, overlap=ov)
+            sol.advance_batch_async(6, overlap=ov)
             e1.record(sol.stream)
             torch.cuda.synchronize()
             sol.finish_advance_batch()
@@ -562,30 +639,15 @@ def run_bench(args, METRIC, UNIT):
     overlap = mode_ms[True] <= mode_ms[False]
     if os.environ.get("AMRB_OVERLAP"):
         overlap = os.environ["AMRB_OVERLAP"] != "0"
-    # AMRB_GRAPH=1: the timed batches replay a CUDA graph of the K-step batch (K even)
-    use_graph = (K % 2 == 0) and os.environ.get("AMRB_GRAPH", "0") == "1"
-    if use_graph:
-        try:
-            sol.advance_batch_graph(K, overlap)              # records, then one untimed replay
-            torch.cuda.synchronize()
-            sol.finish_advance_batch()
-        except Exception as e:                               # noqa: BLE001 - report and fall back
-            sys.stderr.write("rank %d: graph capture failed (%r), eager launches instead\n" % (rank, e))
-            use_graph = False
-    flag = torch.tensor([1 if use_graph else 0], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    use_graph = bool(int(flag.item()))
-    advance = (lambda k: sol.advance_batch_graph(k, overlap)) if use_graph else \
-        (lambda k: sol.advance_batch_async(k, overlap=overlap))
+    advance = lambda k: sol.advance_batch_async(k, overlap=overlap)  # noqa: E731
 
     clocks = bench_mod.ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.25)
-    REPS = 3
-    reps = []
+    reps, total = [], 0.0
     t0w = time.time()
-    for _ in range(REPS):
+    while len(reps) < 3 or (total < 500.0 and len(reps) < 400):
         l0 = sol.launches
         dist.barrier()
         torch.cuda.synchronize()
@@ -598,74 +660,82 @@ def run_bench(args, METRIC, UNIT):
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # max over ranks
         reps.append(float(ms.item()))
+        total += reps[-1]
         launches = sol.launches - l0
     t1w = time.time()
-    ms_total = sorted(reps)[REPS // 2]
+    ms_total = sorted(reps)[len(reps) // 2]
     value = cells * K / (ms_total * 1e-3)
 
     # e2e: pinned-host state -> device, halo, K steps, state back to the host (per rank its shard)
-    n_own = sol.plan.n_owned
-    pinned = [torch.zeros(n_own * sol.pool.flat, dtype=torch.float64).pin_memory() for _ in range(cfg.nvar)]
+    n_own, stored = sol.plan.n_owned, sol.pool.stored
+    fbytes = n_own * stored * 8
+    bufs, how = bench_mod.host_state_buffers(torch, fbytes, cfg.nvar)
     L = sol.L
     for f in range(cfg.nvar):
-        B.check(L.amrb_copy_device_to_host(pinned[f].data_ptr(), L.amrb_pool_field(sol.pool.h, f),
-                                           n_own * sol.pool.flat * 8))
+        B.check(L.amrb_copy_device_to_host(bufs[f].data_ptr(), L.amrb_pool_field(sol.pool.h, f), fbytes))
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(sol.stream)
     for f in range(cfg.nvar):
-        B.check(L.amrb_copy_host_to_device_async(L.amrb_pool_field(sol.pool.h, f), pinned[f].data_ptr(),
-                                                 n_own * sol.pool.flat * 8, L.amrb_pool_stream(sol.pool.h)))
+        B.check(L.amrb_copy_host_to_device_async(L.amrb_pool_field(sol.pool.h, f), bufs[f].data_ptr(),
+                                                 fbytes, L.amrb_pool_stream(sol.pool.h)))
+    sol.pool.mark_dirty()                                    # raw writes: drop the carried dt-min
     sol.halo_exchange()
-    sol.advance_batch_async(K, overlap=overlap)              # eager: the state was just replaced
+    sol.advance_batch_async(K, overlap=overlap)
     for f in range(cfg.nvar):
-        B.check(L.amrb_copy_device_to_host_async(pinned[f].data_ptr(), L.amrb_pool_field(sol.pool.h, f),
-                                                 n_own * sol.pool.flat * 8, L.amrb_pool_stream(sol.pool.h)))
+        B.check(L.amrb_copy_device_to_host_async(bufs[f].data_ptr(), L.amrb_pool_field(sol.pool.h, f),
+                                                 fbytes, L.amrb_pool_stream(sol.pool.h)))
     e1.record(sol.stream)
     torch.cuda.synchronize()
     sol.finish_advance_batch()
     ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    state_bytes = cfg.nvar * n_own * sol.pool.flat * 8
-    tot = torch.tensor([float(state_bytes), float(sol.exchanged_bytes // 2)], dtype=torch.float64, device="cuda")
+    state_bytes = cfg.nvar * fbytes
+    tot = torch.tensor([float(state_bytes), float(sol.exchanged_bytes // 2), float(len(sol.plan.ghost_global)),
+                        float(len(sol.plan.boundary))], dtype=torch.float64, device="cuda")
+    mx = tot.clone()
     dist.all_reduce(tot)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     if rank == 0:
         clk = clocks.stop(t0w, t1w)
         peaks, peak_src = bench_mod.measured_peaks()
         b_alg = 2 * cfg.nvar * 8
         achieved = value * b_alg / 1e9 / world
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 family, weak-scaled: 2D static multi-level tree, Euler fp64, 64x64 "
-                                   "patches halo 1, base level %d + 2 rings (r=%.4f L), Morton-range "
-                                   "partition over %d GPUs" % (base, radius, world),
-                       "cells": int(cells), "patches": int(P), "cells_per_gpu": int(cells // world),
-                       "l2_policy": "inputs larger than L2 (0.8 GB of state per GPU vs 126 MB)",
-                       "executed_steps": int(executed), "launch_mode": "cuda graph replay of the K-step batch"
-                       if use_graph else "eager launches",
+        if strong and args.workload == "c3":
+            cfgobj = bench_mod.workload_config(wl, "c3", world, cells)
+        elif strong:
+            cfgobj = {"workload": "development: C3 family at base level %d" % base, "cells": int(cells)}
+        else:
+            cfgobj = {"workload": "C2 family, weak-scaled: 2D static multi-level tree, Euler fp64, 64x64 "
+                                  "patches halo 1, base level %d + 2 rings (r=%.4f L), Morton-range "
+                                  "partition over %d GPUs" % (base, radius, world), "cells": int(cells),
+                      "l2_policy": "inputs larger than L2 (0.8 GB of state per GPU vs 126 MB)"}
+        cfgobj.update({"patches": int(P), "cells_per_gpu": int(cells // world), "executed_steps": int(executed),
+                       "partition": "contiguous Morton ranges, equal patch counts, %d GPUs" % world,
+                       "device_layout": "interior-only [P][S^3] per field" if storage else "padded",
+                       "launch_mode": "eager launches",
                        "exchange_schedule": "interior patches overlap the slab exchange" if overlap else
                        "exchange, then one launch over all patches",
-                       "schedule_probe_ms_per_10_steps": {"overlap": mode_ms[True], "single_launch": mode_ms[False]}, "ghost_patches_rank0": int(len(sol.plan.ghost_global)),
-                       "ghost_bytes_per_step_all_ranks": float(tot[1].item())},
+                       "schedule_probe_ms_per_6_steps": {"overlap": mode_ms[True], "single_launch": mode_ms[False]},
+                       "ghost_patches_max_rank": int(mx[2].item()), "boundary_patches_max_rank": int(mx[3].item()),
+                       "ghost_bytes_per_step_all_ranks": float(tot[1].item())})
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgobj,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": bench_mod.load_traffic(),
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
                          "kernel": "whole step per GPU (pack + all_to_all + fused kernels + unpack + all-reduce min)",
                          "algorithmic_bytes_per_cell": b_alg, "peak_source": peak_src},
-            "cpu_baseline": None,
+            "cpu_baseline": None, "parity": parity,
             "e2e": {"value": cells * K / (float(ems.item()) * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": float(tot[0].item()) / K, "d2h_bytes_per_step": float(tot[0].item()) / K + 8,
-                    "ms_total": float(ems.item())},
-            "gpu_launches": int(launches), "clocks": clk, "repetitions_ms": reps,
+                    "ms_total": float(ems.item()), "host_buffers": how},
+            "gpu_launches": int(launches), "clocks": clk, "batch_ms": bench_mod.spread(reps),
+            "timed_region_s": total * 1e-3,
         }
         print(json.dumps(line))
     dist.barrier()
-    if use_graph:
-        sol.graphs.clear()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
     sol.pool.close()
     dist.destroy_process_group()

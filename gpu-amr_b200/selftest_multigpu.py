@@ -26,9 +26,10 @@ def main():
     else:
         cfg = wl.Config(3, 8, 1, 5, amrb.EQ_EULER)
         host = wl.build_static_tree(cfg, 2, (0.3,))
+    storage = amrb.STORAGE_INTERIOR if name.endswith("interior") else amrb.STORAGE_PADDED
     steps = 7
     ids = host.ids()
-    sol = mg.ShardedSolver(cfg, host, rank, world, local, dist, torch)
+    sol = mg.ShardedSolver(cfg, host, rank, world, local, dist, torch, storage=storage)
     sol.upload_interior(wl.initial_condition(sol.ids, cfg))
     sol.halo_exchange()
     for overlap in (True, False):
@@ -44,13 +45,18 @@ def main():
     else:
         sol.advance_batch_async(6, overlap=False)
     acc, n, dts = sol.finish_advance_batch(6)
+    # a batch longer than any before: the library re-allocates its per-step scalar arrays, the views of
+    # the dt-min slots the all-reduce writes through must follow (stale views = every rank steps with its
+    # LOCAL CFL minimum and the shards drift apart)
+    sol.advance_batch_async(70)
+    acc, n, dts = sol.finish_advance_batch(70)
     mine = sol.download_interior()
     halo = np.stack([sol.pool.download(f, sol.plan.n_owned) for f in range(cfg.nvar)])
     gathered = [None] * world
     dist.all_gather_object(gathered, (mine, halo, acc, n))
     ok = True
     if rank == 0:
-        lay = amrb.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth)
+        lay = amrb.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage)
         pool = amrb.DevicePool(lay, len(ids), local)
         pool.set_physics([cfg.length] * 3, cfg.gamma, cfg.cfl)
         pool.set_topology(*host.tables())
@@ -58,7 +64,7 @@ def main():
         for f in range(cfg.nvar):
             pool.upload_interior(f, ic[f])
         pool.halo_exchange()
-        for st in (steps, steps, 6, 6):
+        for st in (steps, steps, 6, 6, 70):
             pool.advance_batch_async(st)
             acc1, n1, _ = pool.finish_advance_batch(st)
         ref = np.stack([pool.download_interior(f, len(ids)) for f in range(cfg.nvar)])

@@ -19,7 +19,7 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("case", ["2d", "3d"])
+@pytest.mark.parametrize("case", ["2d", "3d", "3d_interior"])
 def test_sharded_matches_single_gpu(case):
     n = _ngpu()
     if n < 2:
@@ -33,7 +33,7 @@ def test_sharded_matches_single_gpu(case):
     assert "PARITY" in r.stdout
 
 
-@pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 2), ("3d", 5)])
+@pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 2), ("3d", 5), ("3d_interior", 3)])
 def test_sharding_logic_in_one_process(case, world):
     """The sharded path on ONE GPU: W shards of a multi-level mesh (Morton ranges, ghost slots, slab
     pack / unpack, interior / boundary launches, per-step CFL minimum) driven phase by phase in this
@@ -56,9 +56,10 @@ def test_sharding_logic_in_one_process(case, world):
     else:
         cfg = wl.Config(3, 8, 1, 5, amrb.EQ_EULER)
         host = wl.build_static_tree(cfg, 2, (0.3,))
+    storage = amrb.STORAGE_INTERIOR if case.endswith("interior") else amrb.STORAGE_PADDED
     ids = host.ids()
     steps = 5
-    cl = mg.LocalCluster(cfg, host, world, 0, torch)
+    cl = mg.LocalCluster(cfg, host, world, 0, torch, storage=storage)
     for s in cl.sols:
         s.upload_interior(wl.initial_condition(s.ids, cfg))
     cl.halo_exchange()
@@ -67,7 +68,7 @@ def test_sharding_logic_in_one_process(case, world):
     goth = np.concatenate([np.stack([s.pool.download(f, s.plan.n_owned) for f in range(cfg.nvar)])
                            for s in cl.sols], axis=1)
 
-    pool = amrb.DevicePool(amrb.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth), len(ids))
+    pool = amrb.DevicePool(amrb.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage), len(ids))
     pool.set_physics([cfg.length] * 3, cfg.gamma, cfg.cfl)
     pool.set_topology(*host.tables())
     ic = wl.initial_condition(ids, cfg)
@@ -93,7 +94,7 @@ def test_sharding_logic_in_one_process(case, world):
     pool.close()
 
 
-@pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 3)])
+@pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 3), ("3d_interior", 3)])
 def test_reslicing_after_reconstruct_in_one_process(case, world):
     """Active AMR on a sharded mesh, on ONE GPU through LocalCluster: steps, the criterion
     on every shard, one global reconstruct (refine + coarsen + 2:1 ripple), re-slicing — old patches move
@@ -117,9 +118,10 @@ def test_reslicing_after_reconstruct_in_one_process(case, world):
         cfg = wl.Config(3, 8, 1, 5, amrb.EQ_EULER)
         base, radii, thr = 2, (0.3,), (0.62, 0.52)
     steps, cap = 4, 4096
+    storage = amrb.STORAGE_INTERIOR if case.endswith("interior") else amrb.STORAGE_PADDED
 
     # single pool (the checker of this test)
-    one = amrb.DeviceTree(cfg, capacity=cap)
+    one = amrb.DeviceTree(cfg, capacity=cap, storage=storage)
     host0 = wl.build_static_tree(cfg, base, radii)
     # replay the same refinement history on the DeviceTree's own host tree
     for _ in range(base):
@@ -135,7 +137,7 @@ def test_reslicing_after_reconstruct_in_one_process(case, world):
 
     # W shards in this process
     host = wl.build_static_tree(cfg, base, radii)
-    cl = mg.LocalCluster(cfg, host, world, 0, torch, capacity=cap)
+    cl = mg.LocalCluster(cfg, host, world, 0, torch, capacity=cap, storage=storage)
     for s in cl.sols:
         s.upload_interior(wl.initial_condition(s.ids, cfg))
     cl.halo_exchange()

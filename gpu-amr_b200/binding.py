@@ -89,6 +89,7 @@ def lib():
         "amrb_pool_set_physics": [vp, C.POINTER(C.c_double), C.c_double, C.c_double],
         "amrb_pool_upload": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_download": [vp, C.c_int, sz, sz, dp],
+        "amrb_pool_upload_next": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_upload_interior": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_download_interior": [vp, C.c_int, sz, sz, dp],
         "amrb_pool_halo_exchange": [vp],

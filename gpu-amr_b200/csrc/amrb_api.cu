@@ -936,6 +936,31 @@ amrb_status amrb_pool_upload(amrb_pool* p, int field, size_t first, size_t n, co
     p->carry_valid = false;
     return AMRB_OK;
 }
+amrb_status amrb_pool_upload_next(amrb_pool* p, int field, size_t first, size_t n, const double* host)
+{
+    AMRB_TRY(check_range(p, field, first, n, host));
+    AMRB_TRY(set_device(p));
+    if (p->batch_open) return fail(AMRB_ERR_STATE, "a batch is open");
+    if (p->dense)
+    {
+        const size_t chunk = stage_chunk(p);
+        for (size_t s = 0; s < n; s += chunk)
+        {
+            const size_t m = std::min(chunk, n - s);
+            AMRB_TRY(ensure_stage(p, m * p->pflat));
+            AMRB_CUDA(cudaMemcpyAsync(p->d_stage, host + s * p->pflat, m * p->pflat * sizeof(double),
+                                      cudaMemcpyHostToDevice, p->stream));
+            p->ops->interior(p->stream, p->d_stage, p->nxt.p[field] + (first + s) * p->flat, (int)m, 0);
+            AMRB_TRY(check_launch(p, "interior_copy_kernel"));
+            AMRB_CUDA(cudaStreamSynchronize(p->stream));
+        }
+        return AMRB_OK;
+    }
+    AMRB_CUDA(cudaMemcpyAsync(p->nxt.p[field] + first * p->flat, host, n * p->flat * sizeof(double),
+                              cudaMemcpyHostToDevice, p->stream));
+    AMRB_CUDA(cudaStreamSynchronize(p->stream));
+    return AMRB_OK;
+}
 amrb_status amrb_pool_download(amrb_pool* p, int field, size_t first, size_t n, double* host)
 {
     AMRB_TRY(check_range(p, field, first, n, host));

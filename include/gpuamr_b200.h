@@ -154,6 +154,10 @@ amrb_status amrb_pool_upload(amrb_pool* pool, int field, size_t first_patch, siz
                              const double* host);
 amrb_status amrb_pool_download(amrb_pool* pool, int field, size_t first_patch, size_t n_patches,
                                double* host);
+/* the same into the NEXT buffer, for host-side steppers that fill ndtree::get_out_patch<Map, next_buffer>
+ * and then call swap_buffers (ndtree.hpp:516-559, 1558-1579); blocking */
+amrb_status amrb_pool_upload_next(amrb_pool* pool, int field, size_t first_patch, size_t n_patches,
+                                  const double* host);
 /* interior-only variants (host array is [n_patches][prod(size)]) */
 amrb_status amrb_pool_upload_interior(amrb_pool* pool, int field, size_t first_patch,
                                       size_t n_patches, const double* host);

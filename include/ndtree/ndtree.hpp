@@ -17,6 +17,8 @@
 #include "cuda/amrb_check.hpp"
 #include "gpuamr_b200.h"
 #include "intergrid_operator.hpp"
+#include "ndconcepts.hpp"
+#include "neighbor.hpp"
 #include "patch.hpp"
 #include "patch_layout.hpp"
 #include "patch_utils.hpp"
@@ -29,6 +31,8 @@
 #include <stdexcept>
 #include <tuple>
 #include <type_traits>
+#include <utility>
+#include <variant>
 #include <vector>
 
 namespace amr::ndt::tree
@@ -61,6 +65,10 @@ public:
     using fields_t             = typename Cell::deconstructed_types_map_t;
     template <typename Map>
     using patch_t = patches::patch<typename Map::type, patch_layout_t>;
+    // direction system and neighbor variants (ndtree/neighbor.hpp; reference ndtree.hpp:100-125)
+    using patch_direction_t               = neighbors::direction<size_type{ patch_index_t::rank() }>;
+    using neighbor_patch_index_variant_t  = neighbors::neighbor_variant<size_type{ 2 }, size_type{ patch_index_t::rank() }, patch_index_t>;
+    using neighbor_linear_index_variant_t = neighbors::neighbor_variant<size_type{ 2 }, size_type{ patch_index_t::rank() }, linear_index_t>;
 
     enum struct RefinementStatus : std::int8_t
     {
@@ -109,6 +117,7 @@ public:
         amrb_pool_destroy(m_pool);
         amrb_tree_destroy(m_topo);
         amrb_host_pinned_free(m_host);
+        if (m_host_next != nullptr) amrb_host_pinned_free(m_host_next);
         amrb_device_free(m_device_refine_status);
     }
 
@@ -136,6 +145,85 @@ public:
         return static_cast<refine_status_t>(m_status[i]);
     }
 
+    // ---- neighbor queries (reference ndtree.hpp:681-725).  Views decoded from the same tables the device
+    // kernels read (amrb_tree_tables), fetched once per topology
+    [[nodiscard]] auto get_neighbor_at(linear_index_t i, patch_direction_t const& d) const -> neighbor_patch_index_variant_t
+    {
+        using V = neighbor_patch_index_variant_t;
+        const auto l = neighbor_linear_at(i, d);
+        return std::visit(
+            [this](auto const& n) -> V
+            {
+                using N = std::remove_cvref_t<decltype(n)>;
+                using L = neighbor_linear_index_variant_t;
+                if constexpr (std::is_same_v<N, typename L::same>)
+                    return V{ typename V::same{ m_ids[n.id] } };
+                else if constexpr (std::is_same_v<N, typename L::coarser>)
+                    return V{ typename V::coarser{ m_ids[n.id], n.contact_quadrant } };
+                else if constexpr (std::is_same_v<N, typename L::finer>)
+                {
+                    typename V::finer f{};
+                    for (size_type k = 0; k != f.ids.size(); ++k) f.ids[k] = m_ids[n.ids[k]];
+                    return V{ f };
+                }
+                else
+                    return V{};
+            },
+            l.data);
+    }
+    [[nodiscard]] auto get_neighbor_at(patch_index_t const& id, patch_direction_t const& d) const -> neighbor_patch_index_variant_t
+    {
+        return get_neighbor_at(get_linear_index_at(id), d);
+    }
+    [[nodiscard]] auto neighbor_linear_index(neighbor_patch_index_variant_t const& n) const -> neighbor_linear_index_variant_t
+    {
+        using V = neighbor_patch_index_variant_t;
+        using L = neighbor_linear_index_variant_t;
+        return std::visit(
+            [this](auto const& v) -> L
+            {
+                using N = std::remove_cvref_t<decltype(v)>;
+                if constexpr (std::is_same_v<N, typename V::same>)
+                    return L{ typename L::same{ get_linear_index_at(v.id) } };
+                else if constexpr (std::is_same_v<N, typename V::coarser>)
+                    return L{ typename L::coarser{ get_linear_index_at(v.id), v.contact_quadrant } };
+                else if constexpr (std::is_same_v<N, typename V::finer>)
+                {
+                    typename L::finer f{};
+                    for (size_type k = 0; k != f.ids.size(); ++k) f.ids[k] = get_linear_index_at(v.ids[k]);
+                    return L{ f };
+                }
+                else
+                    return L{};
+            },
+            n.data);
+    }
+    // the same query in linear indices, straight from the tables
+    [[nodiscard]] auto neighbor_linear_at(linear_index_t i, patch_direction_t const& d) const -> neighbor_linear_index_variant_t
+    {
+        using L = neighbor_linear_index_variant_t;
+        ensure_host_tables();
+        constexpr size_type ND = 2 * s_rank, KF = size_type{ 1 } << (s_rank - 1);
+        const size_type     e  = i * ND + static_cast<size_type>(d.index());
+        switch (m_rel[e])
+        {
+        case AMRB_REL_SAME: return L{ typename L::same{ static_cast<linear_index_t>(m_nbr[e * KF]) } };
+        case AMRB_REL_FINER:
+        {
+            typename L::finer f{};
+            for (size_type k = 0; k != KF; ++k) f.ids[k] = static_cast<linear_index_t>(m_nbr[e * KF + k]);
+            return L{ f };
+        }
+        case AMRB_REL_COARSER:
+        {
+            typename L::coarser c{ static_cast<linear_index_t>(m_nbr[e * KF]), {} };
+            for (size_type k = 0; k != s_rank; ++k) c.contact_quadrant[k] = static_cast<size_type>(m_quad[e * s_rank + k]);
+            return L{ c };
+        }
+        default: return L{};
+        }
+    }
+
     // ---- host view of the CURRENT buffer (staging mirror, lazily coherent)
     template <typename Map>
     [[nodiscard]] auto get_patch(linear_index_t i) -> patch_t<Map>&
@@ -159,6 +247,46 @@ public:
     [[nodiscard]] auto get_patch(patch_index_t const& id) const -> patch_t<Map> const&
     {
         return get_patch<Map>(get_linear_index_at(id));
+    }
+
+    // ---- explicit buffer selection (reference ndtree.hpp:516-559).  next_buffer is a second host mirror,
+    // allocated on first use: a host-side stepper fills it and calls swap_buffers(), which uploads it into
+    // the device's next buffer before the pointer swap.
+    template <typename Map, auto Buffer>
+    [[nodiscard]] auto get_out_patch(linear_index_t i) -> patch_t<Map>&
+    {
+        static_assert(Buffer == current_buffer || Buffer == next_buffer, "unknown buffer tag");
+        if constexpr (Buffer == current_buffer)
+            return get_patch<Map>(i);
+        else
+        {
+            ensure_host_next();
+            m_host_next_modified = true;
+            return reinterpret_cast<patch_t<Map>*>(m_host_next + field_index<Map>() * m_capacity * s_flat)[i];
+        }
+    }
+    template <typename Map, auto Buffer>
+    [[nodiscard]] auto get_out_patch(patch_index_t const& id) -> patch_t<Map>&
+    {
+        return get_out_patch<Map, Buffer>(get_linear_index_at(id));
+    }
+    // current <-> next (reference ndtree.hpp:1558-1579): pointer swap on the device
+    auto swap_buffers() -> void
+    {
+        make_device_current();
+        if (m_host_next_modified)
+        {
+            static_assert(sizeof(double) == 8);
+            for (size_type f = 0; f != s_nvar; ++f)
+                check(amrb_pool_upload_next(m_pool, static_cast<int>(f), 0, size(), m_host_next + f * m_capacity * s_flat),
+                      "swap_buffers");
+        }
+        check(amrb_pool_swap_buffers(m_pool), "swap_buffers");
+        if (m_host_next != nullptr) std::swap(m_host, m_host_next);
+        // the mirror of the new current buffer is exact only if the host just wrote all of it
+        m_device_newer       = !m_host_next_modified;
+        m_host_modified      = false;
+        m_host_next_modified = false;
     }
 
     // ---- device view (CUDA-mode extras of the reference)
@@ -281,6 +409,28 @@ private:
         // copy + one kernel) instead of the reference's host loop + metadata upload
         // (ndtree.hpp:1606-1700)
         check(amrb_pool_set_topology_from_ids(m_pool, raw, n), "amrb_pool_set_topology_from_ids");
+        m_host_tables_valid = false;
+    }
+
+    auto ensure_host_tables() const -> void
+    {
+        if (m_host_tables_valid) return;
+        constexpr size_type ND = 2 * s_rank, KF = size_type{ 1 } << (s_rank - 1);
+        const size_type     n  = m_ids.size();
+        m_lvl.resize(n);
+        m_rel.resize(n * ND);
+        m_nbr.resize(n * ND * KF);
+        m_quad.resize(n * ND * s_rank);
+        check(amrb_tree_tables(m_topo, m_lvl.data(), m_rel.data(), m_nbr.data(), m_quad.data()), "amrb_tree_tables");
+        m_host_tables_valid = true;
+    }
+    auto ensure_host_next() -> void
+    {
+        if (m_host_next != nullptr) return;
+        void* host = nullptr;
+        check(amrb_host_pinned_malloc(&host, m_capacity * s_flat * s_nvar * sizeof(double)), "host mirror (next)");
+        m_host_next = static_cast<double*>(host);
+        std::memset(m_host_next, 0, m_capacity * s_flat * s_nvar * sizeof(double));
     }
 
     size_type                  m_capacity;
@@ -288,6 +438,11 @@ private:
     amrb_tree*                 m_topo = nullptr;
     amrb_pool*                 m_pool = nullptr;
     double*                    m_host = nullptr; // [field][capacity][flat], pinned
+    double*                    m_host_next = nullptr; // mirror of the next buffer (get_out_patch), lazily allocated
+    bool                       m_host_next_modified = false;
+    mutable std::vector<std::int32_t> m_lvl, m_nbr; // host copy of the neighbor tables (get_neighbor_at)
+    mutable std::vector<std::int8_t>  m_rel, m_quad;
+    mutable bool                      m_host_tables_valid = false;
     std::int8_t*               m_device_refine_status = nullptr;
     std::vector<patch_index_t> m_ids;
     std::vector<std::int8_t>   m_status;

@@ -109,6 +109,16 @@ def lib():
         "amrb_pool_batch_end": [vp, C.c_int],
         "amrb_pool_pack_faces": [vp, i32p, sz, dp],
         "amrb_pool_unpack_faces": [vp, i32p, sz, dp],
+        "amrb_exchange_create": [vp, C.c_int, C.c_int, i32p, vp, vp, i32p, sz, C.POINTER(vp)],
+        "amrb_exchange_destroy": [vp],
+        "amrb_ipc_export": [vp, vp],
+        "amrb_ipc_open": [vp, C.POINTER(vp)],
+        "amrb_ipc_close": [vp],
+        "amrb_exchange_connect": [vp, C.c_int, vp, vp, vp],
+        "amrb_exchange_halo": [vp],
+        "amrb_exchange_advance_batch_async": [vp, sz, C.c_double],
+        "amrb_exchange_push": [vp, C.c_int, sz],
+        "amrb_exchange_wait": [vp, C.c_int, sz],
         "amrb_pool_apply_plan": [vp, sz, i8p, i32p, i8p],
         "amrb_pool_patch_max_flags": [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, i8p],
         "amrb_patch_max_flags_device": [vp, vp, sz, sz, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp],
@@ -143,6 +153,12 @@ def lib():
     L.amrb_pool_levels.restype = vp
     L.amrb_pool_dtmin_slot.argtypes = [vp, sz]
     L.amrb_pool_dtmin_slot.restype = vp
+    L.amrb_exchange_buffer.argtypes = [vp, C.c_int]
+    L.amrb_exchange_buffer.restype = vp
+    L.amrb_exchange_timed_out.argtypes = [vp]
+    L.amrb_exchange_timed_out.restype = C.c_int
+    L.amrb_exchange_launch_count.argtypes = [vp]
+    L.amrb_exchange_launch_count.restype = C.c_uint64
     L.amrb_pool_launch_count.argtypes = [vp]
     L.amrb_pool_launch_count.restype = C.c_uint64
     L.amrb_pool_face_slab_doubles.argtypes = [vp, C.c_int]

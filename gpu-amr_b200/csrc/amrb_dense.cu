@@ -50,13 +50,17 @@ struct DenseInst
         {
             // variant (amrb_pool_set_variant): ring shape A/B.  0 = chunks of 4 planes (2 KB bulk copies),
             // 2 stages (8^3) / 1-plane cp.async chunks, 4 stages (16^3); 21 = 2-plane chunks, 3 stages;
-            // 22 = 2-plane chunks, 2 stages, 3 CTAs per SM (12 warps)
+            // 22 = 2-plane chunks, 2 stages, 3 CTAs per SM (12 warps); 23 / 24 = 10 / 9 warps per SM
             if constexpr (S == 8)
             {
                 if (a.variant == 21)
                     march<2, 3, 4, 2>(st, a, n_items);
                 else if (a.variant == 22)
                     march<2, 2, 4, 3>(st, a, n_items);
+                else if (a.variant == 23)
+                    march<2, 3, 5, 2>(st, a, n_items); // 10 warps per SM, <= 204 registers
+                else if (a.variant == 24)
+                    march<4, 2, 3, 3>(st, a, n_items); // 9 warps per SM, <= 224 registers
                 else
                     march<4, 2, 4, 2>(st, a, n_items);
             }

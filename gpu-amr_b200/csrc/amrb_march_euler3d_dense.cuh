@@ -418,7 +418,8 @@ euler3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
                 rB[f] = fma(hz, GzB[f], pv.accB[f]);
                 if (fin) *reinterpret_cast<double2*>(a.nxt.p[f] + go) = make_double2(rA[f], rB[f]);
             }
-            if (fin) go += SS;
+            if (!fin) return; // plane 0: `pv` is the ghost plane below (warp-uniform branch)
+            go += SS;
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2)
             {
@@ -430,9 +431,9 @@ euler3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
                 K *= 0.5 * irho;
                 const double pr = gm1 * (n[4] - K);
                 const double cs = sqrt_nr2(g * pr * irho);
-                sxm             = fin ? pos_max(sxm, fabs(n[1] * irho) + cs) : sxm;
-                sym             = fin ? pos_max(sym, fabs(n[2] * irho) + cs) : sym;
-                szm             = fin ? pos_max(szm, fabs(n[3] * irho) + cs) : szm;
+                sxm             = pos_max(sxm, fabs(n[1] * irho) + cs);
+                sym             = pos_max(sym, fabs(n[2] * irho) + cs);
+                szm             = pos_max(szm, fabs(n[3] * irho) + cs);
             }
         };
 

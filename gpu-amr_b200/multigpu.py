@@ -67,6 +67,11 @@ class ShardPlan:
         self.recv_counts = np.bincount(rcv[:, 0], minlength=world).astype(np.int64)
         self.send_global = snd[:, 2:4].copy()
         self.recv_global = rcv[:, 2:4].copy()
+        # peer-memory exchange: where this rank's segment starts inside rank q's receive buffer
+        # (= the entries ranks below this one send to q; receive buffers are ordered by source rank)
+        pair = np.zeros((world, world), dtype=np.int64)
+        np.add.at(pair, (ent[:, 0], ent[:, 1]), 1)
+        self.send_offsets = np.array([pair[:rank, q].sum() for q in range(world)], dtype=np.int64)
         assert (self.send_entries[:, 0] >= 0).all() and (self.send_entries[:, 0] < self.n_owned).all()
         assert (self.recv_entries[:, 0] >= self.n_owned).all()
 
@@ -149,9 +154,15 @@ class ShardedSolver:
     """One rank's share of the mesh on one GPU."""
 
     def __init__(self, cfg, host_tree, rank, world, device, dist, torch, capacity=None,
-                 storage=B.STORAGE_PADDED):
+                 storage=B.STORAGE_PADDED, transport="nccl"):
+        """transport: "nccl" = pack -> all_to_all_single -> unpack + all_reduce(min), driven from here;
+        "p2p" = the library's peer-memory exchange (amrb_exchange_*: slabs stored straight into the peers'
+        receive buffers over NVLink, flags + CFL minimum in peer mailboxes, K-step loop in C++)."""
         self.cfg, self.rank, self.world, self.dist, self.torch = cfg, rank, world, dist, torch
         self.device = device
+        self.transport = transport
+        self.ex = None
+        self._peer_maps = []
         levels, rel, nbr, quad = host_tree.tables()
         self.plan = pl = ShardPlan(levels, rel, nbr, quad, rank, world)
         self.ids = host_tree.ids()[pl.lo:pl.hi]
@@ -195,6 +206,71 @@ class ShardedSolver:
         self.exchanged_bytes = (sum(self.in_splits) + sum(self.out_splits)) * 8
         self.graphs = {}
         self._dtmin_cache = {}
+        if self.transport == "p2p":
+            self._install_p2p()
+
+    # ---- peer-memory exchange (include/gpuamr_b200.h section 6b)
+    def _install_p2p(self):
+        import ctypes as C
+        L, pl = self.L, self.plan
+        self._drop_p2p()
+        ex = C.c_void_p()
+        sc = np.ascontiguousarray(pl.send_counts, np.int64)
+        so = np.ascontiguousarray(pl.send_offsets, np.int64)
+        se = np.ascontiguousarray(pl.send_entries, np.int32)
+        re = np.ascontiguousarray(pl.recv_entries, np.int32)
+        B.check(L.amrb_exchange_create(self.pool.h, self.rank, self.world, B._ptr(se), B._ptr(sc), B._ptr(so),
+                                       B._ptr(re), len(re), C.byref(ex)))
+        self.ex = ex
+        if self.dist is None:
+            return                       # in-process cluster: LocalCluster connects the raw pointers
+        handles = []
+        for which in range(3):
+            buf = (C.c_ubyte * 64)()
+            B.check(L.amrb_ipc_export(L.amrb_exchange_buffer(ex, which), buf))
+            handles.append(bytes(buf))
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, handles)
+        err = None
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                ptrs = []
+                for hb in gathered[r]:
+                    out = C.c_void_p()
+                    src = (C.c_ubyte * 64).from_buffer_copy(hb)
+                    B.check(L.amrb_ipc_open(src, C.byref(out)))
+                    ptrs.append(out)
+                    self._peer_maps.append(out)
+                B.check(L.amrb_exchange_connect(ex, r, ptrs[0], ptrs[1], ptrs[2]))
+        except B.AmrbError as e:         # e.g. no peer access between two GPUs of this box
+            err = str(e)
+        oks = [None] * self.world
+        self.dist.all_gather_object(oks, err)
+        if any(o is not None for o in oks):
+            # every rank falls back together: the exchange driven from here over torch.distributed
+            import sys
+            if self.rank == 0:
+                sys.stderr.write("peer-memory exchange unavailable (%s): NCCL transport instead\n"
+                                 % next(o for o in oks if o is not None))
+            self._drop_p2p()
+            self.transport = "nccl"
+
+    def _drop_p2p(self):
+        if self.ex is not None:
+            self.torch.cuda.synchronize()
+            if self.dist is not None:
+                self.dist.barrier()      # nobody may still be pushing into buffers about to be unmapped
+            for m in self._peer_maps:
+                self.L.amrb_ipc_close(m)
+            self._peer_maps = []
+            self.L.amrb_exchange_destroy(self.ex)
+            self.ex = None
+
+    def close(self):
+        self._drop_p2p()
+        self.pool.close()
 
     # ---- re-slicing after a reconstruct
     def field_views(self, which):
@@ -272,6 +348,10 @@ class ShardedSolver:
                                    self.out_splits, self.in_splits)
 
     def exchange(self):
+        if self.ex is not None:
+            B.check(self.L.amrb_exchange_halo(self.ex))
+            self.launches += 3
+            return
         self._pack()
         self._comm()
         self.stream.wait_stream(self.comm_stream)
@@ -315,6 +395,11 @@ class ShardedSolver:
 
     def advance_batch_async(self, steps, remaining=B.DBL_MAX, overlap=True):
         L, h, pl = self.L, self.pool.h, self.plan
+        if self.ex is not None:
+            l0 = int(L.amrb_exchange_launch_count(self.ex)) + self.pool.launch_count()
+            B.check(L.amrb_exchange_advance_batch_async(self.ex, steps, remaining))
+            self.launches += int(L.amrb_exchange_launch_count(self.ex)) + self.pool.launch_count() - l0
+            return
         B.check(L.amrb_pool_batch_begin(h, steps, remaining))
         self._allreduce_dtmin(0)
         for k in range(steps):
@@ -366,7 +451,10 @@ class ShardedSolver:
         self.launches += self.graph_launches
 
     def finish_advance_batch(self, max_steps=0):
-        return self.pool.finish_advance_batch(max_steps)
+        out = self.pool.finish_advance_batch(max_steps)
+        if self.ex is not None and self.L.amrb_exchange_timed_out(self.ex):
+            raise B.AmrbError("peer-memory exchange: a rank stopped answering (receiver timed out)")
+        return out
 
 
 # ------------------------------------------------------------------------------- in-process cluster
@@ -377,10 +465,15 @@ class LocalCluster:
     copies.  Test vehicle for the sharding logic on a single-GPU box (the NCCL transport itself is
     covered by tests/test_multigpu_gpu.py on >= 2 GPUs)."""
 
-    def __init__(self, cfg, host_tree, world, device, torch, capacity=None, storage=B.STORAGE_PADDED):
+    def __init__(self, cfg, host_tree, world, device, torch, capacity=None, storage=B.STORAGE_PADDED,
+                 transport="copy"):
+        """transport "copy": slabs moved by device-to-device copies of the packed buffers (the NCCL path's
+        stand-in); "p2p": the library's peer-memory exchange with the peers' buffers connected as plain
+        pointers (same device), driven push-all / wait-all because all ranks share this process."""
         self.torch, self.world, self.cfg = torch, world, cfg
+        self.p2p = transport == "p2p"
         self.sols = [ShardedSolver(cfg, host_tree, r, world, device, None, torch, capacity=capacity,
-                                   storage=storage)
+                                   storage=storage, transport="p2p" if self.p2p else "nccl")
                      for r in range(world)]
         self._index_exchange()
 
@@ -391,11 +484,30 @@ class LocalCluster:
         for r, s in enumerate(self.sols):
             for q, t in enumerate(self.sols):
                 assert s.in_splits[q] == t.out_splits[r], "send / receive plans disagree"
+        if self.p2p:
+            L = self.sols[0].L
+            for r, s in enumerate(self.sols):
+                for q, t in enumerate(self.sols):
+                    if q != r:
+                        B.check(L.amrb_exchange_connect(s.ex, q, L.amrb_exchange_buffer(t.ex, 0),
+                                                        L.amrb_exchange_buffer(t.ex, 1),
+                                                        L.amrb_exchange_buffer(t.ex, 2)))
 
     def _sync(self):
         self.torch.cuda.synchronize()
 
+    def _p2p_exchange(self, with_dt=0, k=0):
+        L = self.sols[0].L
+        for s in self.sols:                                  # every push is enqueued before any wait
+            B.check(L.amrb_exchange_push(s.ex, with_dt, k))
+        for s in self.sols:
+            B.check(L.amrb_exchange_wait(s.ex, with_dt, k))
+
     def exchange(self):
+        if self.p2p:
+            self._p2p_exchange()
+            self._sync()
+            return
         for s in self.sols:
             s._pack()
         self._sync()
@@ -429,9 +541,13 @@ class LocalCluster:
         for s in self.sols:
             B.check(L.amrb_pool_batch_begin(s.pool.h, steps, B.DBL_MAX))
         self._sync()
-        self._reduce_dtmin(0)
+        if not self.p2p:
+            self._reduce_dtmin(0)
         for k in range(steps):
-            self.exchange()
+            if self.p2p:
+                self._p2p_exchange(1, k)                     # slabs + CFL minimum of slot k in one exchange
+            else:
+                self.exchange()
             for s in self.sols:
                 pl, h = s.plan, s.pool.h
                 if overlap:
@@ -442,7 +558,8 @@ class LocalCluster:
                 else:
                     B.check(L.amrb_pool_step_partial(h, None, 0))
             self._sync()
-            self._reduce_dtmin(k + 1)
+            if not self.p2p:
+                self._reduce_dtmin(k + 1)
             for s in self.sols:
                 B.check(L.amrb_pool_step_commit(s.pool.h))
         self.exchange()
@@ -482,7 +599,7 @@ class LocalCluster:
 
     def close(self):
         for s in self.sols:
-            s.pool.close()
+            s.close()
 
 
 # ---------------------------------------------------------------------------------------- bench
@@ -600,7 +717,8 @@ def run_bench(args, METRIC, UNIT):
     else:
         cfg, host, base, radius = weak_scaled_tree(wl, world)
         storage = B.STORAGE_PADDED
-    sol = ShardedSolver(cfg, host, rank, world, local, dist, torch, storage=storage)
+    sol = ShardedSolver(cfg, host, rank, world, local, dist, torch, storage=storage,
+                        transport=os.environ.get("AMRB_TRANSPORT", "p2p"))
     P = host.size
     cells = P * cfg.data
     parity_ok, parity = check_parity(torch, dist, bench_mod, amrb, wl, cfg, host, sol, rank, world, local, storage)
@@ -608,7 +726,7 @@ def run_bench(args, METRIC, UNIT):
         if rank == 0:
             sys.stderr.write("PARITY FAILURE (sharded vs single pool): %s\n" % json.dumps(parity))
         dist.barrier()
-        sol.pool.close()
+        sol.close()
         dist.destroy_process_group()
         raise SystemExit(3)
     bench_mod.fill_ic(torch, amrb, wl, sol.pool, sol.ids, cfg, local)
@@ -715,8 +833,12 @@ def run_bench(args, METRIC, UNIT):
                        "partition": "contiguous Morton ranges, equal patch counts, %d GPUs" % world,
                        "device_layout": "interior-only [P][S^3] per field" if storage else "padded",
                        "launch_mode": "eager launches",
-                       "exchange_schedule": "interior patches overlap the slab exchange" if overlap else
-                       "exchange, then one launch over all patches",
+                       "transport": "peer-memory push over NVLink (slabs + CFL minimum + flag in one kernel), "
+                                    "K-step loop in the library" if sol.transport == "p2p" else
+                                    "NCCL all_to_all_single + all_reduce(min) driven from Python",
+                       "exchange_schedule": "push, wait, unpack, one launch over all patches" if sol.transport == "p2p"
+                       else ("interior patches overlap the slab exchange" if overlap else
+                             "exchange, then one launch over all patches"),
                        "schedule_probe_ms_per_6_steps": {"overlap": mode_ms[True], "single_launch": mode_ms[False]},
                        "ghost_patches_max_rank": int(mx[2].item()), "boundary_patches_max_rank": int(mx[3].item()),
                        "ghost_bytes_per_step_all_ranks": float(tot[1].item())})
@@ -726,7 +848,7 @@ def run_bench(args, METRIC, UNIT):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgobj,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                         "kernel": "whole step per GPU (pack + all_to_all + fused kernels + unpack + all-reduce min)",
+                         "kernel": "whole step per GPU (slab push / exchange + wait + unpack + fused step kernel)",
                          "algorithmic_bytes_per_cell": b_alg, "peak_source": peak_src},
             "cpu_baseline": None, "parity": parity,
             "e2e": {"value": cells * K / (float(ems.item()) * 1e-3), "unit": UNIT,
@@ -737,5 +859,5 @@ def run_bench(args, METRIC, UNIT):
         }
         print(json.dumps(line))
     dist.barrier()
-    sol.pool.close()
+    sol.close()
     dist.destroy_process_group()

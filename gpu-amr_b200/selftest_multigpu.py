@@ -29,7 +29,10 @@ def main():
     storage = amrb.STORAGE_INTERIOR if name.endswith("interior") else amrb.STORAGE_PADDED
     steps = 7
     ids = host.ids()
-    sol = mg.ShardedSolver(cfg, host, rank, world, local, dist, torch, storage=storage)
+    transport = sys.argv[2] if len(sys.argv) > 2 else "nccl"
+    sol = mg.ShardedSolver(cfg, host, rank, world, local, dist, torch, storage=storage, transport=transport)
+    if transport == "p2p" and sol.transport != "p2p":
+        raise SystemExit("the peer-memory exchange could not be set up on this box")
     sol.upload_interior(wl.initial_condition(sol.ids, cfg))
     sol.halo_exchange()
     for overlap in (True, False):
@@ -78,8 +81,8 @@ def main():
         mask = (outside <= 1).ravel()
         ok = np.array_equal(got, ref) and np.array_equal(goth[..., mask], refh[..., mask])
         ok = ok and all(g[2] == acc1 and g[3] == n1 for g in gathered)
-        print("multigpu selftest %s world=%d patches=%d: %s (sum dt %.17g, steps %d)"
-              % (name, world, len(ids), "PARITY" if ok else "MISMATCH", acc1, n1))
+        print("multigpu selftest %s [%s] world=%d patches=%d: %s (sum dt %.17g, steps %d)"
+              % (name, sol.transport, world, len(ids), "PARITY" if ok else "MISMATCH", acc1, n1))
         pool.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
@@ -90,7 +93,7 @@ def main():
         torch.cuda.synchronize()
         sys.stdout.flush()
         os._exit(rc)
-    sol.pool.close()
+    sol.close()
     dist.destroy_process_group()
     sys.exit(rc)
 

@@ -245,6 +245,43 @@ amrb_status amrb_pool_unpack_faces(amrb_pool* pool, const int32_t* dev_entries, 
                                    const double* dev_buffer);
 
 /* ------------------------------------------------------------------------------------------
+ * 6b. the same exchange over peer-mapped memory (NVLink / NVSwitch), no collective library on the data
+ *    path: per step ONE kernel gathers the slabs, stores them straight into the peers' receive buffers,
+ *    drops this rank's CFL minimum into the peers' mailboxes and raises its arrival flag there; the
+ *    receiver acquire-spins on the flags (one warp, bounded by a timeout), folds the minima (= the
+ *    all-reduce(min) of dt) and unpacks locally.  The K-step loop runs inside the library.
+ *    Setup: every rank creates its exchange from its ShardPlan lists, exports its mailbox and its two
+ *    receive buffers (amrb_exchange_buffer + amrb_ipc_export), opens the peers' handles (amrb_ipc_open; in
+ *    one process: the peers' pointers as they are) and connects them.  world <= 8.
+ *      send_entries [n_send][2] = {owned patch, face}, sorted by destination rank (send_counts[world]);
+ *      send_offsets[r] = entries ranks below this one send to r (where this rank's segment starts there);
+ *      recv_entries [n_recv][2] = {ghost slot, face} in arrival order (source rank, then the sender's order).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct amrb_exchange amrb_exchange;
+amrb_status amrb_exchange_create(amrb_pool* pool, int rank, int world, const int32_t* send_entries,
+                                 const int64_t* send_counts, const int64_t* send_offsets,
+                                 const int32_t* recv_entries, size_t n_recv, amrb_exchange** out);
+amrb_status amrb_exchange_destroy(amrb_exchange* ex);
+/* which: 0 = mailbox, 1 / 2 = receive buffer of generation parity 0 / 1 (device pointers of THIS rank) */
+void*       amrb_exchange_buffer(amrb_exchange* ex, int which);
+amrb_status amrb_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle: 64 bytes */
+amrb_status amrb_ipc_open(const void* handle64, void** dev_ptr);   /* maps a peer process's buffer  */
+amrb_status amrb_ipc_close(void* dev_ptr);
+amrb_status amrb_exchange_connect(amrb_exchange* ex, int peer, void* mailbox, void* recv0, void* recv1);
+/* one exchange of the current buffers' slabs into the peers' ghost slots; asynchronous */
+amrb_status amrb_exchange_halo(amrb_exchange* ex);
+/* amrb_pool_advance_batch_async over the sharded mesh: per step push + wait/fold + unpack + fused step;
+ * ends with an exchange and the halo materialisation.  Read back with amrb_pool_finish_advance_batch. */
+amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, double remaining_time);
+/* the two halves of one exchange (drivers that interleave several ranks in one process); with_dt folds the
+ * CFL minimum of slot k of the open batch */
+amrb_status amrb_exchange_push(amrb_exchange* ex, int with_dt, size_t k);
+amrb_status amrb_exchange_wait(amrb_exchange* ex, int with_dt, size_t k);
+/* 1 when a receiver gave up waiting for a peer since the last call (state undefined afterwards) */
+int         amrb_exchange_timed_out(amrb_exchange* ex);
+uint64_t    amrb_exchange_launch_count(const amrb_exchange* ex);
+
+/* ------------------------------------------------------------------------------------------
  * 7. host topology — Morton-ordered leaf set, refine/coarsen with 2:1 balancing and the
  *    neighbor tables derived from it.  Replaces the host side of ndtree::reconstruct_tree
  *    (ndtree.hpp:886-940, 1127-1271) and neighbor maintenance (ndtree/neighbor.hpp:291-572)

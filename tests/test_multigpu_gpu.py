@@ -19,22 +19,24 @@ def _ngpu():
         return 0
 
 
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
 @pytest.mark.parametrize("case", ["2d", "3d", "3d_interior"])
-def test_sharded_matches_single_gpu(case):
+def test_sharded_matches_single_gpu(case, transport):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29631",
-           os.path.join(ROOT, "gpu-amr_b200", "selftest_multigpu.py"), case]
+           os.path.join(ROOT, "gpu-amr_b200", "selftest_multigpu.py"), case, transport]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PARITY" in r.stdout
 
 
+@pytest.mark.parametrize("transport", ["copy", "p2p"])
 @pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 2), ("3d", 5), ("3d_interior", 3)])
-def test_sharding_logic_in_one_process(case, world):
+def test_sharding_logic_in_one_process(case, world, transport):
     """The sharded path on ONE GPU: W shards of a multi-level mesh (Morton ranges, ghost slots, slab
     pack / unpack, interior / boundary launches, per-step CFL minimum) driven phase by phase in this
     process, slabs moved by device-to-device copies instead of NCCL.  State, materialised halos and
@@ -59,7 +61,7 @@ def test_sharding_logic_in_one_process(case, world):
     storage = amrb.STORAGE_INTERIOR if case.endswith("interior") else amrb.STORAGE_PADDED
     ids = host.ids()
     steps = 5
-    cl = mg.LocalCluster(cfg, host, world, 0, torch, storage=storage)
+    cl = mg.LocalCluster(cfg, host, world, 0, torch, storage=storage, transport=transport)
     for s in cl.sols:
         s.upload_interior(wl.initial_condition(s.ids, cfg))
     cl.halo_exchange()

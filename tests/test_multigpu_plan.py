@@ -56,6 +56,8 @@ def test_plans_are_mutually_consistent(amrb, world, cfgname):
         for q, pq in enumerate(plans):
             ro = np.concatenate([[0], np.cumsum(pq.recv_counts)])
             assert np.array_equal(p.send_global[so[q]:so[q + 1]], pq.recv_global[ro[r]:ro[r + 1]])
+            # peer-memory exchange: r's segment inside q's receive buffer starts where q expects it
+            assert p.send_offsets[q] == ro[r]
         # every remote (patch, face) a halo will read is received
         need = set()
         for i in p.boundary:

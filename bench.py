@@ -441,6 +441,20 @@ def run_ours(args):
     wl = importlib.import_module("gpu-amr_b200.workloads")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c5":
+        # BASELINE configs[4]: 3D active-AMR advection (development line, not the driver's bench line)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(local)
+        aa = importlib.import_module("gpu-amr_b200.active_amr")
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        aa.bench_c5(args, torch, METRIC, UNIT, ClockSampler, measured_peaks, dist)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if world > 1:
         mg = importlib.import_module("gpu-amr_b200.multigpu")
         return mg.run_bench(args, METRIC, UNIT)

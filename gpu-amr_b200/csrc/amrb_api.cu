@@ -6,6 +6,7 @@
 #include "amrb_step_euler.cuh"
 #include "amrb_march_euler.cuh"
 #include "amrb_march_euler3d.cuh"
+#include "amrb_advect2d.cuh"
 
 #include "../../include/gpuamr_b200.h"
 
@@ -199,7 +200,24 @@ struct Inst
                 <<<(tiles + TPC - 1) / TPC, ENT, EC::SMEM, st>>>(a, n_items);
         }
         else
+        {
+            if constexpr (R == 2)
+            {
+                // warp-autonomous streaming kernel (amrb_advect2d.cuh); AMRB_VARIANT 10 = thread per cell
+                if (a.variant != 10)
+                {
+                    using AC = Adv2Cfg<S, H, 4>;
+                    auto k   = advect2d_kernel<S, H, 4, 3>;
+                    static DevicePrepared prepared;
+                    if (!prepared.ensure((const void*)k, (int)AC::SMEM)) return;
+                    const int tasks = AC::WHOLE ? (n_items + AC::TP - 1) / AC::TP : n_items * AC::NB;
+                    const int grid  = std::max(1, std::min(sm_count() * 3, (tasks + 3) / 4));
+                    k<<<grid, 128, AC::SMEM, st>>>(a, n_items);
+                    return;
+                }
+            }
             step_v1(st, a, n_items);
+        }
     }
     static void compute_dt(cudaStream_t st, const StepArgs& a, unsigned long long* out)
     {

@@ -33,6 +33,17 @@ struct DenseInst
         const int grid  = std::max(1, std::min(device_sm_count() * MINB, (tasks + WPC - 1) / WPC));
         k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
     }
+    template <int CR, int NS, int WPC, int MAXREG, int CTAS>
+    static void march_r(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        using MC = March3DenseCfg<S, CR, NS, WPC>;
+        auto k   = euler3d_dense_kernel_r<S, CR, NS, WPC, MAXREG>;
+        static DevicePrepared prepared;
+        if (!prepared.ensure((const void*)k, (int)MC::SMEM)) return;
+        const int tasks = n_items * MC::NB;
+        const int grid  = std::max(1, std::min(device_sm_count() * CTAS, (tasks + WPC - 1) / WPC));
+        k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
+    }
     template <int WPC, int MINB>
     static void advect(cudaStream_t st, const StepArgs& a, int n_items)
     {
@@ -50,17 +61,20 @@ struct DenseInst
         {
             // variant (amrb_pool_set_variant): ring shape A/B.  0 = chunks of 4 planes (2 KB bulk copies),
             // 2 stages (8^3) / 1-plane cp.async chunks, 4 stages (16^3); 21 = 2-plane chunks, 3 stages;
-            // 22 = 2-plane chunks, 2 stages, 3 CTAs per SM (12 warps); 23 / 24 = 10 / 9 warps per SM
+            // 22 = 2-plane chunks, 2 stages, 3 CTAs per SM (12 warps); 25 / 26 / 27 = 10 / 9 / 12 warps per SM
+            // with explicit register budgets (__maxnreg__)
             if constexpr (S == 8)
             {
                 if (a.variant == 21)
                     march<2, 3, 4, 2>(st, a, n_items);
                 else if (a.variant == 22)
                     march<2, 2, 4, 3>(st, a, n_items);
-                else if (a.variant == 23)
-                    march<2, 3, 5, 2>(st, a, n_items); // 10 warps per SM, <= 204 registers
-                else if (a.variant == 24)
-                    march<4, 2, 3, 3>(st, a, n_items); // 9 warps per SM, <= 224 registers
+                else if (a.variant == 25)
+                    march_r<2, 3, 5, 200, 2>(st, a, n_items); // 10 warps per SM, 200 registers
+                else if (a.variant == 26)
+                    march_r<4, 2, 3, 224, 3>(st, a, n_items); // 9 warps per SM, 224 registers
+                else if (a.variant == 27)
+                    march_r<2, 2, 6, 168, 2>(st, a, n_items); // 12 warps per SM as 2 CTAs of 6 warps
                 else
                     march<4, 2, 4, 2>(st, a, n_items);
             }

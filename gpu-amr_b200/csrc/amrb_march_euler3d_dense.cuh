@@ -47,9 +47,8 @@ struct March3DenseCfg
     static_assert((FS * 8) % 16 == 0 && (WARP_DOUBLES * 8) % 16 == 0, "bulk copy alignment");
 };
 
-template <int S, int CR, int NS, int WPC, int MINB>
-__global__ void __launch_bounds__(WPC * 32, MINB)
-euler3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
+template <int S, int CR, int NS, int WPC>
+__device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_items)
 {
     using C           = March3DenseCfg<S, CR, NS, WPC>;
     constexpr int NV  = 5;
@@ -625,6 +624,21 @@ euler3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
         for (int o = 16; o > 0; o >>= 1) cand = fmin(cand, __shfl_xor_sync(0xffffffffu, cand, o));
         if (lane == 0 && kc > 0) atomicMin(a.sc.dtmin_out, (unsigned long long)__double_as_longlong(cand));
     }
+}
+
+// occupancy by CTAs per SM (register budget = 64 K / (MINB x CTA threads rounded up to 128))
+template <int S, int CR, int NS, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+euler3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
+{
+    euler3d_dense_body<S, CR, NS, WPC>(a, n_items);
+}
+// occupancy by an explicit register budget (CTA sizes that are not multiples of 128 threads)
+template <int S, int CR, int NS, int WPC, int MAXREG>
+__global__ void __launch_bounds__(WPC * 32) __maxnreg__(MAXREG)
+euler3d_dense_kernel_r(const __grid_constant__ StepArgs a, int n_items)
+{
+    euler3d_dense_body<S, CR, NS, WPC>(a, n_items);
 }
 
 } // namespace amrb

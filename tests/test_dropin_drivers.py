@@ -44,6 +44,22 @@ def test_reference_3d_benchmark_driver_reproduces_cpu_run():
     assert (_field(out, "Min patch count"), _field(out, "Max patch count")) == (64, 23136)
 
 
+def test_reference_active_amr_benchmark_driver_reproduces_cpu_run():
+    """BASELINE config C4 (bench_fvm_solver_integration_active_amr.b.cpp: reconstruct_tree every 2 steps,
+    thresholds 0.512 / 0.506, levels 1-7, two pulses): 1 313 reconstructs, 351 of them changing the topology,
+    every refinement decision taken by the device criterion.  Golden = the reference's own CPU run
+    (tests/golden/counts/, 65 minutes on one core)."""
+    gold = open(os.path.join(ROOT, "tests", "golden", "counts",
+                             "ref_bench_fvm_solver_integration_active_amr.cpu.txt")).read()
+    out = _run("ref_bench_fvm_solver_integration_active_amr")
+    assert "CUDA ENABLED" in out and "CUDA DISABLED" in gold
+    for label in ("Updated cells", "Solver timesteps", "Initial reconstructions", "Timed reconstructions",
+                  "Identity reconstructions", "Topology-changing reconstructions", "Final patch count",
+                  "Min patch count", "Max patch count"):
+        assert _field(out, label) == _field(gold, label), label
+    assert _field(gold, "Updated cells") == 39271899136 and _field(gold, "Topology-changing reconstructions") == 351
+
+
 def test_advection_pulse_property_checks():
     out = _run("advection_pulse_check")
     assert "ALL OK" in out and out.count(": OK") == 2

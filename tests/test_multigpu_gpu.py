@@ -34,6 +34,23 @@ def test_sharded_matches_single_gpu(case, transport):
     assert "PARITY" in r.stdout
 
 
+@pytest.mark.parametrize("storage,transport", [("interior", "p2p"), ("interior", "nccl"), ("padded", "p2p")])
+def test_active_amr_sharded_matches_single_gpu(storage, transport):
+    """BASELINE config C5 family on >= 2 GPUs: criterion on every shard, one global reconstruct, re-slicing of
+    the Morton ranges (whole old patches travel between curve neighbours), new tables / ghost slots / exchange
+    lists -- against the same loop on one pool (gpu-amr_b200/selftest_active_amr.py)."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29633",
+           os.path.join(ROOT, "gpu-amr_b200", "selftest_active_amr.py"), storage, transport]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PARITY" in r.stdout
+
+
 @pytest.mark.parametrize("transport", ["copy", "p2p"])
 @pytest.mark.parametrize("case,world", [("2d", 3), ("3d", 2), ("3d", 5), ("3d_interior", 3)])
 def test_sharding_logic_in_one_process(case, world, transport):

@@ -23,7 +23,7 @@
 namespace amrb
 {
 
-template <int S, int H, int WPC>
+template <int S, int H, int WPC, int BRB = 8>
 struct Adv2Cfg
 {
     using G                    = Geo<2, S, H>;
@@ -31,7 +31,7 @@ struct Adv2Cfg
     static constexpr int FLAT  = G::FLAT;
     static constexpr bool WHOLE = (FLAT * 8 <= 4096);                       // whole padded patches per task
     static constexpr int TP    = WHOLE ? ((6400 / (FLAT * 8)) > 0 ? (6400 / (FLAT * 8)) : 1) : 1;
-    static constexpr int BR    = WHOLE ? S : 8;                             // interior rows per task
+    static constexpr int BR    = WHOLE ? S : BRB;                           // interior rows per task
     static constexpr int NB    = S / BR;                                    // tasks per patch (band mode)
     static constexpr int NR    = WHOLE ? P : BR + 2;                        // staged rows per patch
     static constexpr int ROW0  = WHOLE ? H : 1;                             // staged row of the task's first interior row
@@ -48,11 +48,11 @@ struct Adv2Cfg
     static_assert((PST * 8) % 16 == 0 && (P * 8) % 16 == 0, "bulk copy size / alignment (padded extents are even)");
 };
 
-template <int S, int H, int WPC, int MINB>
+template <int S, int H, int WPC, int MINB, int BRB = 8>
 __global__ void __launch_bounds__(WPC * 32, MINB)
 advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
 {
-    using C          = Adv2Cfg<S, H, WPC>;
+    using C          = Adv2Cfg<S, H, WPC, BRB>;
     using G          = Geo<2, S, H>;
     constexpr int P = C::P, FLAT = C::FLAT, TP = C::TP, BR = C::BR, PST = C::PST, GP = C::GP;
 
@@ -221,27 +221,75 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
             cand = fmin(cand, fmin(a.dx[lvl][0] / 1.0, a.dx[lvl][1] / 0.5));
             const double* tile = st + j * PST;
             double*       out  = nxt + (size_t)p * FLAT + (size_t)(H + r0) * P;
-#pragma unroll 4
-            for (int e = lane; e < BR * P; e += 32)
+            if constexpr (H == 1)
             {
-                const int r = e / P, c = e % P;
-                const int cc = min(max(c, H), H + S - 1);
-                const int o  = (C::ROW0 + r) * P + cc;
-                const double u = tile[o];
-                double       upd = 0.0;
+                // a lane owns two x-adjacent cells: the 16-byte aligned pairs (2i, 2i+1) of the padded row.
+                // First pair = (ghost | first cell), last pair = (last cell | ghost): the ghost gets a copy.
+                constexpr int HP = P / 2;
+#pragma unroll 2
+                for (int q = lane; q < BR * HP; q += 32)
                 {
-                    const double v = 1.0, uL = tile[o - 1], uR = tile[o + 1];
-                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                    upd -= cx * (fR - fL);
+                    const int  r = q / HP, pc = q % HP, c = 2 * pc;
+                    const int  o = (C::ROW0 + r) * P + c;
+                    const bool first = (pc == 0), last = (pc == HP - 1);
+                    const double2 ct = *reinterpret_cast<const double2*>(tile + o);
+                    const double2 dn = *reinterpret_cast<const double2*>(tile + o - P);
+                    const double2 up = *reinterpret_cast<const double2*>(tile + o + P);
+                    const double  lf = tile[first ? o : o - 1];
+                    const double  rg = tile[last ? o + 1 : o + 2];
+                    double nv[2];
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2)
+                    {
+                        const double u = s2 ? ct.y : ct.x;
+                        double       upd = 0.0;
+                        {
+                            const double v = 1.0, uL = s2 ? ct.x : lf, uR = s2 ? rg : ct.y;
+                            const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                            const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                            upd -= cx * (fR - fL);
+                        }
+                        {
+                            const double v = 0.5, uL = s2 ? dn.y : dn.x, uR = s2 ? up.y : up.x;
+                            const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                            const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                            upd -= cy * (fR - fL);
+                        }
+                        nv[s2] = u + upd;
+                    }
+                    *reinterpret_cast<double2*>(out + r * P + c) = make_double2(first ? nv[1] : nv[0], last ? nv[0] : nv[1]);
                 }
+            }
+            else
+            {
+                int r = lane / P, c = lane % P; // element (row, padded column) walked incrementally
+                for (int e = lane; e < BR * P; e += 32)
                 {
-                    const double v = 0.5, uL = tile[o - P], uR = tile[o + P];
-                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                    upd -= cy * (fR - fL);
+                    const int    cc = min(max(c, H), H + S - 1);
+                    const int    o  = (C::ROW0 + r) * P + cc;
+                    const double u  = tile[o];
+                    double       upd = 0.0;
+                    {
+                        const double v = 1.0, uL = tile[o - 1], uR = tile[o + 1];
+                        const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                        const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                        upd -= cx * (fR - fL);
+                    }
+                    {
+                        const double v = 0.5, uL = tile[o - P], uR = tile[o + P];
+                        const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
+                        const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
+                        upd -= cy * (fR - fL);
+                    }
+                    out[e] = u + upd;
+                    r += 32 / P;
+                    c += 32 % P;
+                    if (c >= P)
+                    {
+                        c -= P;
+                        ++r;
+                    }
                 }
-                out[e] = u + upd;
             }
         }
         // park the ghost cells of the next task (their loads were in flight during the compute loop)

@@ -203,16 +203,29 @@ struct Inst
         {
             if constexpr (R == 2)
             {
-                // warp-autonomous streaming kernel (amrb_advect2d.cuh); AMRB_VARIANT 10 = thread per cell
-                if (a.variant != 10)
+                // warp-autonomous streaming kernel (amrb_advect2d.cuh).  variant 10 = thread per cell;
+                // 41 / 42 = 8- / 16-row bands of the streaming kernel for wide patches (default: patches
+                // wider than 16 cells keep the thread-per-cell kernel, narrower ones stream in groups)
+                const bool wide = (S > 16);
+                if (a.variant != 10 && (!wide || a.variant == 41 || a.variant == 42))
                 {
-                    using AC = Adv2Cfg<S, H, 4>;
-                    auto k   = advect2d_kernel<S, H, 4, 3>;
-                    static DevicePrepared prepared;
-                    if (!prepared.ensure((const void*)k, (int)AC::SMEM)) return;
-                    const int tasks = AC::WHOLE ? (n_items + AC::TP - 1) / AC::TP : n_items * AC::NB;
-                    const int grid  = std::max(1, std::min(sm_count() * 3, (tasks + 3) / 4));
-                    k<<<grid, 128, AC::SMEM, st>>>(a, n_items);
+                    auto launch = [&](auto kern, size_t smem, int tasks, int wpc, int ctas) {
+                        static DevicePrepared prepared;
+                        if (!prepared.ensure((const void*)kern, (int)smem)) return;
+                        const int grid = std::max(1, std::min(sm_count() * ctas, (tasks + wpc - 1) / wpc));
+                        kern<<<grid, wpc * 32, smem, st>>>(a, n_items);
+                    };
+                    if (wide && a.variant == 42)
+                    {
+                        using AC = Adv2Cfg<S, H, 4, (S % 16 == 0 ? 16 : 8)>;
+                        launch(advect2d_kernel<S, H, 4, 2, (S % 16 == 0 ? 16 : 8)>, AC::SMEM, n_items * AC::NB, 4, 2);
+                    }
+                    else
+                    {
+                        using AC = Adv2Cfg<S, H, 4>;
+                        launch(advect2d_kernel<S, H, 4, 3>, AC::SMEM,
+                               AC::WHOLE ? (n_items + AC::TP - 1) / AC::TP : n_items * AC::NB, 4, 3);
+                    }
                     return;
                 }
             }
@@ -1372,6 +1385,232 @@ amrb_status amrb_patch_max_flags_device(const double* dev_field, const int32_t* 
 }
 
 const int32_t* amrb_pool_levels(const amrb_pool* p) { return p ? p->d_level : nullptr; }
+
+// ------------------------------------------------------------------------------ kernel-level entry points
+// (the reference's launch protocol on caller-owned arrays; integration/amrb_shim.cpp)
+namespace
+{
+// the reference's halo_direction_metadata (include/cuda/halo_exchange.hpp:19-26), 36 bytes
+struct RefHaloMeta
+{
+    int32_t neighbor;
+    int32_t finer_ids[4];
+    int32_t quadrant[3];
+    int8_t  relation;
+    int8_t  padding[3];
+};
+static_assert(sizeof(RefHaloMeta) == 36, "reference metadata record");
+
+__global__ void ref_meta_to_tables_kernel(const RefHaloMeta* __restrict__ ref, int count, int rank,
+                                          int32_t* __restrict__ nbr, uint8_t* __restrict__ meta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int         KF = 1 << (rank - 1);
+    const RefHaloMeta r  = ref[i];
+    int               m  = r.relation & 3;
+    for (int k = 0; k < KF; ++k) nbr[(size_t)i * KF + k] = -1;
+    if (m == 1 || m == 3) nbr[(size_t)i * KF] = r.neighbor;
+    if (m == 2)
+        for (int k = 0; k < KF; ++k) nbr[(size_t)i * KF + k] = r.finer_ids[k];
+    if (m == 3)
+        for (int k = 0; k < rank; ++k) m |= (r.quadrant[k] & 1) << (2 + k);
+    meta[i] = (uint8_t)m;
+}
+__global__ void raw_finalize_dt_kernel(double* dt, double* acc, double* remaining, uint32_t* count, double cfl)
+{
+    // finalize_step_dt_kernel semantics (src/cuda/fvm_time_step.cu:204-233)
+    double step = *dt * cfl;
+    if (*remaining <= 0.0)
+        step = 0.0;
+    else if (step > *remaining)
+        step = *remaining;
+    *dt = step;
+    *acc += step;
+    if (step > 0.0)
+    {
+        *remaining -= step;
+        ++*count;
+    }
+}
+__global__ void raw_set_double_kernel(double* p, double v) { *p = v; }
+__global__ void raw_set_uint32_kernel(uint32_t* p, uint32_t v) { *p = v; }
+
+// grow-only device scratch of the raw entry points (tables converted from the reference's metadata, zeroed
+// dummy tables and step scalars); the reference's protocol is single-threaded, default stream
+struct RawScratch
+{
+    int32_t* nbr = nullptr;
+    uint8_t* meta = nullptr;
+    size_t   cap = 0;      // (patch, direction) records
+    double*  scal = nullptr; // [0] remaining = DBL_MAX, [1] dt taken, [2] remaining out
+    unsigned int* queue = nullptr;
+};
+RawScratch g_raw;
+
+amrb_status raw_tables(size_t records, int rank, cudaStream_t st, bool zero)
+{
+    const int KF = 1 << (rank - 1);
+    if (g_raw.cap < records)
+    {
+        cudaFree(g_raw.nbr);
+        cudaFree(g_raw.meta);
+        g_raw.cap = 0;
+        const size_t cap = records * 2;
+        AMRB_CUDA(cudaMalloc(&g_raw.nbr, cap * 4 * sizeof(int32_t)));
+        AMRB_CUDA(cudaMalloc(&g_raw.meta, cap));
+        g_raw.cap = cap;
+    }
+    if (!g_raw.scal)
+    {
+        AMRB_CUDA(cudaMalloc(&g_raw.scal, 4 * sizeof(double)));
+        AMRB_CUDA(cudaMalloc(&g_raw.queue, sizeof(unsigned int)));
+        const double init[4] = { DBL_MAX, 0.0, 0.0, 0.0 };
+        AMRB_CUDA(cudaMemcpy(g_raw.scal, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
+    if (zero)
+    {
+        AMRB_CUDA(cudaMemsetAsync(g_raw.meta, 0, records, st));
+        AMRB_CUDA(cudaMemsetAsync(g_raw.nbr, 0, records * KF * sizeof(int32_t), st));
+    }
+    return AMRB_OK;
+}
+
+amrb_status raw_ops(const amrb_layout* l, const Ops** out)
+{
+    if (!l) return fail(AMRB_ERR_ARGUMENT, "null layout");
+    if (l->storage != AMRB_STORAGE_PADDED) return fail(AMRB_ERR_UNSUPPORTED, "raw entry points work on padded arrays");
+    const Ops* o = find_ops(*l);
+    if (!o) return fail(AMRB_ERR_UNSUPPORTED, "no kernels instantiated for this patch shape / equation");
+    AMRB_CUDA(o->prepare());
+    *out = o;
+    return AMRB_OK;
+}
+
+void raw_step_args(const amrb_layout* l, const double* root, double gamma, StepArgs& a)
+{
+    std::memset(&a, 0, sizeof(a));
+    a.gamma    = gamma;
+    a.task_map = 1;
+    for (int lvl = 0; lvl <= kMaxLevel; ++lvl)
+        for (int d = 0; d < 3; ++d)
+            a.dx[lvl][d] = (d < l->rank) ? root[d] / (double)(1u << std::min(lvl, 30)) : 1.0; // fvm_time_step.cu:54-56
+}
+} // namespace
+
+amrb_status amrb_raw_halo_exchange(const amrb_layout* layout, double* field_base, const void* ref_metadata,
+                                   size_t metadata_count, size_t num_patches, void* stream)
+{
+    if (num_patches == 0) return AMRB_OK;
+    if (!layout || !field_base || !ref_metadata) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (metadata_count != num_patches * 2 * (size_t)layout->rank)
+        return fail(AMRB_ERR_ARGUMENT, "Halo exchange CUDA metadata size mismatch"); // halo_exchange.cu:363-366
+    // one field at a time: the single-field (advection) instantiation of this patch shape
+    amrb_layout one = *layout;
+    one.nvar        = 1;
+    one.equation    = AMRB_EQ_ADVECTION;
+    const Ops* ops  = nullptr;
+    AMRB_TRY(raw_ops(&one, &ops));
+    cudaStream_t st = (cudaStream_t)stream;
+    AMRB_TRY(raw_tables(metadata_count, layout->rank, st, false));
+    ref_meta_to_tables_kernel<<<(unsigned)((metadata_count + 255) / 256), 256, 0, st>>>(
+        static_cast<const RefHaloMeta*>(ref_metadata), (int)metadata_count, layout->rank, g_raw.nbr, g_raw.meta);
+    FieldPtrs f{};
+    f.p[0] = field_base;
+    ops->halo_fill(st, f, g_raw.nbr, g_raw.meta, (int)num_patches);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("halo_kernel: ") + cudaGetErrorString(e));
+    return AMRB_OK;
+}
+
+amrb_status amrb_raw_compute_dt(const amrb_layout* layout, const double* const* fields, const int32_t* levels,
+                                size_t num_patches, const double* root_cell_size, double gamma, double* dev_dt,
+                                void* stream)
+{
+    if (num_patches == 0) return AMRB_OK;
+    if (!layout || !fields || !levels || !root_cell_size || !dev_dt) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    const Ops* ops = nullptr;
+    AMRB_TRY(raw_ops(layout, &ops));
+    cudaStream_t st = (cudaStream_t)stream;
+    StepArgs     a;
+    raw_step_args(layout, root_cell_size, gamma, a);
+    for (int f = 0; f < layout->nvar; ++f) a.cur.p[f] = const_cast<double*>(fields[f]);
+    a.level     = levels;
+    a.n_patches = (int)num_patches;
+    raw_set_double_kernel<<<1, 1, 0, st>>>(dev_dt, DBL_MAX);
+    ops->compute_dt(st, a, reinterpret_cast<unsigned long long*>(dev_dt));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("compute_dt_kernel: ") + cudaGetErrorString(e));
+    return AMRB_OK;
+}
+
+amrb_status amrb_raw_finalize_dt(double* dev_dt, double* dev_accumulator, double* dev_remaining,
+                                 uint32_t* dev_step_count, double cfl, void* stream)
+{
+    if (!dev_dt || !dev_accumulator || !dev_remaining || !dev_step_count) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    raw_finalize_dt_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_dt, dev_accumulator, dev_remaining, dev_step_count, cfl);
+    cudaGetLastError();
+    return AMRB_OK;
+}
+
+amrb_status amrb_raw_time_step(const amrb_layout* layout, double* const* in, double* const* out,
+                               const int32_t* levels, size_t num_patches, const double* root_cell_size,
+                               double gamma, const double* dev_dt, void* stream)
+{
+    if (num_patches == 0) return AMRB_OK;
+    if (!layout || !in || !out || !levels || !root_cell_size || !dev_dt) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    const Ops* ops = nullptr;
+    AMRB_TRY(raw_ops(layout, &ops));
+    cudaStream_t st = (cudaStream_t)stream;
+    // zeroed tables: relation "none" everywhere = the stored ghosts of `in` are used as they are
+    AMRB_TRY(raw_tables(num_patches * 2 * (size_t)layout->rank, layout->rank, st, true));
+    StepArgs a;
+    raw_step_args(layout, root_cell_size, gamma, a);
+    for (int f = 0; f < layout->nvar; ++f)
+    {
+        a.cur.p[f] = in[f];
+        a.nxt.p[f] = out[f];
+    }
+    a.nbr       = g_raw.nbr;
+    a.meta      = g_raw.meta;
+    a.level     = levels;
+    a.n_patches = (int)num_patches;
+    a.lazy_halo = 0;
+    a.variant   = getenv("AMRB_VARIANT") ? atoi(getenv("AMRB_VARIANT")) : 0;
+    // the step size is final at *dev_dt: dt = raw * 1.0, never clamped (remaining = DBL_MAX)
+    a.sc = StepScalars{ reinterpret_cast<const unsigned long long*>(dev_dt), nullptr, g_raw.scal, g_raw.scal + 2,
+                        g_raw.scal + 1, 0.0, 1.0 };
+    if (layout->rank == 3 && layout->equation == AMRB_EQ_EULER)
+    {
+        AMRB_CUDA(cudaMemsetAsync(g_raw.queue, 0, sizeof(unsigned int), st));
+        a.queue = g_raw.queue;
+    }
+    ops->step(st, a, (int)num_patches);
+    if (g_prepare_error != cudaSuccess)
+    {
+        const cudaError_t pe = g_prepare_error;
+        g_prepare_error      = cudaSuccess;
+        return fail(AMRB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(pe));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("step kernel: ") + cudaGetErrorString(e));
+    return AMRB_OK;
+}
+
+amrb_status amrb_raw_set_double(double* dev, double value, void* stream)
+{
+    if (!dev) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    raw_set_double_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev, value);
+    cudaGetLastError();
+    return AMRB_OK;
+}
+amrb_status amrb_raw_set_uint32(uint32_t* dev, uint32_t value, void* stream)
+{
+    if (!dev) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    raw_set_uint32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev, value);
+    cudaGetLastError();
+    return AMRB_OK;
+}
 
 amrb_status amrb_profile_capture_start(void)
 {

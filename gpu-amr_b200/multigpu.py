@@ -642,23 +642,27 @@ def state_checksums(torch, views, bounds, stored):
     return out
 
 
-def check_parity(torch, dist, bench_mod, amrb, wl, cfg, host, sol, rank, world, local, storage, steps=3):
-    """Correctness evidence carried by the bench line itself: the sharded run (pack / exchange / unpack,
-    interior + boundary launches, all-reduced CFL minimum) against ONE pool holding the whole mesh on rank 0,
-    same initial condition, `steps` steps: dt sequence equal, state bit-identical (integer checksums of the
-    bit patterns per field and per rank's Morton range)."""
+def check_parity(torch, dist, bench_mod, amrb, wl, cfg, host, sol, rank, world, local, storage, steps=3,
+                 tol=1e-12):
+    """Correctness evidence carried by the bench line itself: the sharded run (slab exchange, ghost slots,
+    per-step CFL minimum across ranks) against ONE pool holding the whole mesh on rank 0, same initial
+    condition, `steps` steps.  Rank 0 sends every rank the reference state of its Morton range; each rank
+    compares element by element: max |a - b| / max |b| per field (SURVEY 8c metric) must be <= tol, the dt
+    sequence must agree to tol.  Also reports whether the states are bit-identical (they are whenever the
+    shards and the single pool launch the same kernel instantiation; the 2D marching kernel picks its band
+    height from the launch size, which changes rounding in the last bit)."""
     ids_all = host.ids()
-    P, stored = len(ids_all), sol.pool.stored
+    P, stored, nvar = len(ids_all), sol.pool.stored, cfg.nvar
     bench_mod.fill_ic(torch, amrb, wl, sol.pool, sol.ids, cfg, local)
     sol.halo_exchange()
     sol.advance_batch_async(steps)
     _, n_s, dts_s = sol.finish_advance_batch(steps)
     torch.cuda.synchronize()
-    own = [v[:sol.plan.n_owned * stored] for v in sol.field_views("cur")]
-    mine = state_checksums(torch, own, [0, sol.plan.n_owned], stored)[:, 0].contiguous()
-    gathered = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    ok, detail = True, {}
+    n_own = sol.plan.n_owned
+    own = [v[:n_own * stored] for v in sol.field_views("cur")]
+    bounds = [int(b) for b in sol.plan.bounds]
+    detail, views, pool = {}, None, None
+    dts_1 = None
     if rank == 0:
         lay = B.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage)
         pool = B.DevicePool(lay, P, local)
@@ -669,15 +673,45 @@ def check_parity(torch, dist, bench_mod, amrb, wl, cfg, host, sol, rank, world, 
         pool.advance_batch_async(steps)
         _, n_1, dts_1 = pool.finish_advance_batch(steps)
         torch.cuda.synchronize()
-        views = bench_mod.pool_field_views(torch, amrb, pool, P * stored, cfg.nvar)
-        ref = state_checksums(torch, views, sol.plan.bounds, stored).cpu().numpy()      # [field, rank]
-        got = torch.stack(gathered, dim=1).cpu().numpy()
-        state_ok = bool((ref == got).all())
-        dt_ok = bool(n_1 == n_s and np.array_equal(np.asarray(dts_1), np.asarray(dts_s)))
-        ok = state_ok and dt_ok
+        views = bench_mod.pool_field_views(torch, amrb, pool, P * stored, nvar)
+    # element-wise comparison, one field of one rank's range at a time (chunks of <= 2^27 doubles)
+    CH = 1 << 27
+    stats = torch.zeros(3 * nvar, dtype=torch.float64, device="cuda")     # per field: max|a-b|, max|b|, #different
+    buf = torch.empty(min(CH, max(n_own * stored, 1)), dtype=torch.float64, device="cuda") if rank != 0 else None
+    for r in range(world):
+        lo, hi = bounds[r] * stored, bounds[r + 1] * stored
+        for f in range(nvar):
+            for c0 in range(lo, hi, CH):
+                c1 = min(hi, c0 + CH)
+                if rank == 0 and r == 0:
+                    ref, mine = views[f][c0:c1], own[f][c0 - lo:c1 - lo]
+                elif rank == 0:
+                    dist.send(views[f][c0:c1].contiguous(), dst=r)
+                    continue
+                elif rank == r:
+                    ref = buf[:c1 - c0]
+                    dist.recv(ref, src=0)
+                    mine = own[f][c0 - lo:c1 - lo]
+                else:
+                    continue
+                d = (mine - ref).abs()
+                stats[3 * f] = torch.maximum(stats[3 * f], d.max())
+                stats[3 * f + 1] = torch.maximum(stats[3 * f + 1], ref.abs().max())
+                stats[3 * f + 2] += (mine.view(torch.int64) != ref.view(torch.int64)).sum().to(torch.float64)
+    mx = stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(stats)                                   # the #different entries add up
+    ok = True
+    if rank == 0:
+        err = max(float(mx[3 * f]) / max(float(mx[3 * f + 1]), 1e-300) for f in range(nvar))
+        ndiff = int(sum(float(stats[3 * f + 2]) for f in range(nvar)))
+        a, b = np.asarray(dts_s), np.asarray(dts_1)
+        dt_ok = bool(n_1 == n_s and len(a) == len(b) and np.allclose(a, b, rtol=tol, atol=0))
+        ok = bool(err <= tol) and dt_ok
         detail = {"checked": True, "steps": int(steps), "against": "one pool holding the whole mesh on rank 0",
-                  "state_bit_identical": state_ok, "dt_sequence_identical": dt_ok,
-                  "mismatching_field_rank_pairs": int((ref != got).sum())}
+                  "state_max_err_over_field_max": err, "tolerance": tol, "state_bit_identical": ndiff == 0,
+                  "values_differing_in_the_last_bits": ndiff, "dt_sequence_matches": dt_ok,
+                  "dt_sequence_bit_identical": bool(np.array_equal(a, b))}
         pool.close()
         del views
         torch.cuda.empty_cache()

@@ -337,6 +337,35 @@ amrb_status amrb_patch_max_flags_device(const double* dev_field, const int32_t* 
 const int32_t* amrb_pool_levels(const amrb_pool* pool);
 
 /* ------------------------------------------------------------------------------------------
+ * 9. kernel-level entry points on CALLER-OWNED padded device arrays — the reference's own launch protocol
+ *    (one call per kernel of src/cuda/halo_exchange.cu and src/cuda/fvm_time_step.cu), for a build that
+ *    keeps the reference's ndtree.hpp / amr_solver.hpp and replaces only those two translation units
+ *    (integration/amrb_shim.cpp).  Arrays use the reference's device layout
+ *    (field f of patch p at base[f] + p * flat_size); all launches are asynchronous on `stream`
+ *    (NULL = the legacy default stream the reference uses).
+ *      amrb_raw_halo_exchange   halo_exchange_scalar_patches_inplace (include/cuda/halo_exchange.hpp:42-47):
+ *                               ONE field in place; ref_metadata = device array of the reference's 36-byte
+ *                               halo_direction_metadata records, [num_patches * 2 * rank]
+ *      amrb_raw_compute_dt      launch_compute_dt_kernel_device (fvm_time_step.hpp): *dev_dt = min dx / speed
+ *      amrb_raw_finalize_dt     launch_finalize_step_dt: dt *= cfl, clamp to the remaining time, accumulate
+ *      amrb_raw_time_step       launch_time_step_kernel_with_device_dt: in -> out with the step size at
+ *                               *dev_dt, stored face ghosts of `in` trusted (the reference fills them first)
+ *    root_cell_size[d] = cell size of a level-0 patch along solver direction d (x, y, z)
+ *    (time_step_launch_config::root_c_size). */
+amrb_status amrb_raw_halo_exchange(const amrb_layout* layout, double* field_base, const void* ref_metadata,
+                                   size_t metadata_count, size_t num_patches, void* stream);
+amrb_status amrb_raw_compute_dt(const amrb_layout* layout, const double* const* fields, const int32_t* levels,
+                                size_t num_patches, const double* root_cell_size, double gamma,
+                                double* dev_dt, void* stream);
+amrb_status amrb_raw_finalize_dt(double* dev_dt, double* dev_accumulator, double* dev_remaining,
+                                 uint32_t* dev_step_count, double cfl, void* stream);
+amrb_status amrb_raw_time_step(const amrb_layout* layout, double* const* in, double* const* out,
+                               const int32_t* levels, size_t num_patches, const double* root_cell_size,
+                               double gamma, const double* dev_dt, void* stream);
+amrb_status amrb_raw_set_double(double* dev, double value, void* stream);
+amrb_status amrb_raw_set_uint32(uint32_t* dev, uint32_t value, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * 8. profiling hooks — replaces amr::cuda::profile_capture_{start,stop}, profile_range_{push,pop}
  *    (include/cuda/profiler.hpp, src/cuda/device_buffer.cu:229-237)
  * ---------------------------------------------------------------------------------------- */

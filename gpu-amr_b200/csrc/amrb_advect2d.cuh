@@ -125,8 +125,49 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
             t  = (r - 2 * BR) % S;
         }
     };
-    // gather the ghost cells of task k into registers (value NaN-free default: 0, skipped when unused)
-    auto gather = [&](int k, double (&gv)[C::NG]) {
+    // halo tables of a task's patches, 10 ints per patch (8 neighbor indices = 4 directions x 2, the 4 relation
+    // bytes as one word, the level), spread over the lanes (NT3 registers per lane), loaded TWO tasks ahead and
+    // handed round by shuffles.  Looked up per ghost cell they were a chain of three dependent global loads
+    // (relation, neighbor index, value) in front of every gather: ~10 k cycles per 512-cell task.
+    constexpr int NT3 = (TP * 10 + 31) / 32;
+    struct Tabs
+    {
+        int r[NT3];
+    };
+    auto tab_load = [&](int k) -> Tabs {
+        Tabs t;
+#pragma unroll
+        for (int i = 0; i < NT3; ++i) t.r[i] = 0;
+        if (k >= nt) return t;
+        int item0, np, r0;
+        task_of(k, item0, np, r0);
+#pragma unroll
+        for (int i = 0; i < NT3; ++i)
+        {
+            const int w = lane + 32 * i, j = w / 10, c = w % 10;
+            if (j >= np) continue;
+            const int p = patch_of(item0 + j);
+            if (c < 8)
+                t.r[i] = __ldg(a.nbr + (size_t)p * 8 + c);
+            else if (c == 8)
+                t.r[i] = (int)__ldg(reinterpret_cast<const uint32_t*>(a.meta) + p);
+            else
+                t.r[i] = __ldg(a.level + p);
+        }
+        return t;
+    };
+    auto tab_get = [&](const Tabs& t, int w) -> int {
+        int v = __shfl_sync(0xffffffffu, t.r[0], w & 31);
+#pragma unroll
+        for (int i = 1; i < NT3; ++i)
+        {
+            const int u = __shfl_sync(0xffffffffu, t.r[i], w & 31);
+            v           = ((w >> 5) == i) ? u : v;
+        }
+        return v;
+    };
+    // gather the ghost cells of task k into registers (default 0, skipped when unused); tb = its tables
+    auto gather = [&](int k, const Tabs& tb, double (&gv)[C::NG]) {
 #pragma unroll
         for (int i = 0; i < C::NG; ++i) gv[i] = 0.0;
         if (k >= nt || !a.lazy_halo) return;
@@ -136,14 +177,17 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
         for (int i = 0; i < C::NG; ++i)
         {
             const int g = lane + 32 * i;
+            int       j, sd, t;
+            ghost_decode(g < C::GH ? g : 0, j, sd, t);
+            const int d = (sd < 2) ? 2 + sd : sd - 2;  // tree direction: x- = 2, x+ = 3, y- = 0, y+ = 1
+            // all lanes take part in the table shuffles; lanes without a ghost cell skip afterwards
+            const int m = (tab_get(tb, j * 10 + 8) >> (8 * d)) & 0xff;
+            NbRegs<2> nq;
+            nq.v[0] = tab_get(tb, j * 10 + 2 * d);
+            nq.v[1] = tab_get(tb, j * 10 + 2 * d + 1);
             if (g >= np * GP) continue;
-            int j, sd, t;
-            ghost_decode(g, j, sd, t);
             if (sd == 2 && r0 != 0) continue;          // the band does not touch the bottom / top face
             if (sd == 3 && r0 + BR != S) continue;
-            const int p = patch_of(item0 + j);
-            const int d = (sd < 2) ? 2 + sd : sd - 2;  // tree direction: x- = 2, x+ = 3, y- = 0, y+ = 1
-            const int m = (int)__ldg(a.meta + (size_t)p * 4 + d);
             if ((m & 3) == 0) continue;
             int idx[2];
             if (sd < 2)
@@ -156,7 +200,7 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
                 idx[0] = (sd == 3) ? H + S : H - 1;
                 idx[1] = H + t;
             }
-            gv[i] = halo_source<2, S, H>(cur, a.nbr + ((size_t)p * 4 + d) * 2, m, d, idx);
+            gv[i] = halo_source<2, S, H, H, NbRegs<2>>(cur, nq, m, d, idx);
         }
     };
 
@@ -170,8 +214,9 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
     double cand = DBL_MAX;
     double gv[C::NG];
 
+    Tabs tab_cur = tab_load(0), tab_nxt = tab_load(1);
     issue(0);
-    gather(0, gv);
+    gather(0, tab_cur, gv);
 #pragma unroll
     for (int i = 0; i < C::NG; ++i)
         if (lane + 32 * i < C::GH) sG[lane + 32 * i] = gv[i];
@@ -180,7 +225,8 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
     for (int k = 0; k < nt; ++k)
     {
         issue(k + 1);   // stage (k+1)&1 was released at the end of task k-1
-        gather(k + 1, gv);
+        gather(k + 1, tab_nxt, gv);
+        const Tabs tab_nn = tab_load(k + 2); // in flight during this task
         int item0, np, r0;
         task_of(k, item0, np, r0);
         const int b  = k & 1;
@@ -195,14 +241,14 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
             for (int i = 0; i < C::NG; ++i)
             {
                 const int g = lane + 32 * i;
+                int       j, sd, t;
+                ghost_decode(g < C::GH ? g : 0, j, sd, t);
+                const int d = (sd < 2) ? 2 + sd : sd - 2;
+                const int m = (tab_get(tab_cur, j * 10 + 8) >> (8 * d)) & 0xff;
                 if (g >= np * GP) continue;
-                int j, sd, t;
-                ghost_decode(g, j, sd, t);
                 if (sd == 2 && r0 != 0) continue;
                 if (sd == 3 && r0 + BR != S) continue;
-                const int p = patch_of(item0 + j);
-                const int d = (sd < 2) ? 2 + sd : sd - 2;
-                if ((__ldg(a.meta + (size_t)p * 4 + d) & 3) == 0) continue;
+                if ((m & 3) == 0) continue;
                 int o;
                 if (sd < 2)
                     o = (C::ROW0 + t) * P + (sd ? H + S : H - 1);
@@ -216,7 +262,7 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
         for (int j = 0; j < np; ++j)
         {
             const int    p   = patch_of(item0 + j);
-            const int    lvl = __ldg(a.level + p);
+            const int    lvl = tab_get(tab_cur, j * 10 + 9);
             const double cx = dt / a.dx[lvl][0], cy = dt / a.dx[lvl][1]; // amr_solver.hpp:330
             cand = fmin(cand, fmin(a.dx[lvl][0] / 1.0, a.dx[lvl][1] / 0.5));
             const double* tile = st + j * PST;
@@ -300,6 +346,8 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
                 if (lane + 32 * i < C::GH) gn[lane + 32 * i] = gv[i];
         }
         __syncwarp(); // every lane is done with stage b: task k+2 may overwrite it
+        tab_cur = tab_nxt;
+        tab_nxt = tab_nn;
     }
 
     if (a.sc.dtmin_out != nullptr)

@@ -73,8 +73,21 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
     }
     __syncwarp();
 
-    // request task k: the bulk copy of its planes and the gather of its lateral ghost cells
-    auto request = [&](int k) {
+    // halo tables of a task's patch, one 32-bit piece per lane (lanes 0-23: the 6 x 4 neighbor indices, lane 24:
+    // level, lanes 25-30: the 6 relation bytes), loaded TWO tasks ahead and handed round by shuffles: looked up
+    // per ghost cell they were a chain of three dependent global loads (relation, neighbor index, value) in
+    // front of every gather -- ~10 k cycles per 512-cell task, the whole kernel (profiles/r02_summary.md)
+    auto tab_load = [&](int k) -> int {
+        if (k >= nt) return 0;
+        int p, z0;
+        task_of(k, p, z0);
+        if (lane < 24) return __ldg(a.nbr + (size_t)p * 24 + lane);
+        if (lane == 24) return __ldg(a.level + p);
+        if (lane < 31) return (int)__ldg(a.meta + (size_t)p * 6 + (lane - 25));
+        return 0;
+    };
+    // request task k: the bulk copy of its planes and the gather of its lateral ghost cells (tab = its tables)
+    auto request = [&](int k, int tab) {
         if (k >= nt) return;
         int p, z0;
         task_of(k, p, z0);
@@ -90,10 +103,12 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
         {
             const int sd = e / (S * ZT), r = e % (S * ZT), zl = r / S, t = r % S;
             const int d  = (sd < 2) ? 4 + sd : sd;      // tree direction: x-, x+, y-, y+
-            const int m  = (int)__ldg(a.meta + (size_t)p * 6 + d);
-            const int32_t* nb = a.nbr + ((size_t)p * 6 + d) * 4;
+            const int m  = __shfl_sync(0xffffffffu, tab, 25 + d);
             const int rel = m & 3;
             const int z   = z0 + zl;
+            // neighbor index this ghost cell reads: the first one, or for a finer neighbor the one covering it
+            const int nsel = (rel == 2) ? (z / HF) + 2 * (t / HF) : 0;
+            const int nq   = __shfl_sync(0xffffffffu, tab, d * 4 + nsel);
             // interior coordinates of the ghost cell mirrored into the neighbor's frame
             // (patch_utils.hpp:322-327): the normal coordinate -1 -> S-1, S -> 0
             int fy, fx;
@@ -112,8 +127,7 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
                 // finer_t: mean of the 2^3 fine cells of one of the 4 finer neighbors, summed
                 // last-dim-fastest (patch_utils.hpp:334-386, 203-234); finer index = z half + 2 x half of
                 // the other tangential dim (neighbor.hpp:316-337)
-                const int     q = __ldg(nb + (z / HF) + 2 * (t / HF));
-                const double* s = cur + (size_t)q * N + (size_t)((z * 2) % S) * SS + ((fy * 2) % S) * S +
+                const double* s = cur + (size_t)nq * N + (size_t)((z * 2) % S) * SS + ((fy * 2) % S) * S +
                                   ((fx * 2) % S);
                 double sum = 0.0;
                 sum += __ldg(s);
@@ -130,12 +144,12 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
             {
                 size_t o;
                 if (rel == 1)
-                    o = (size_t)__ldg(nb) * N + (size_t)z * SS + fy * S + fx; // same_t
+                    o = (size_t)nq * N + (size_t)z * SS + fy * S + fx; // same_t
                 else if (rel == 3)
                 {
                     // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
                     const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
-                    o = (size_t)__ldg(nb) * N + (size_t)(qz * HF + z / 2) * SS + (qy * HF + fy / 2) * S +
+                    o = (size_t)nq * N + (size_t)(qz * HF + z / 2) * SS + (qy * HF + fy / 2) * S +
                         (qx * HF + fx / 2);
                 }
                 else
@@ -160,15 +174,17 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
     }
     double cand = DBL_MAX;
 
-    request(0);
+    int tab_cur = tab_load(0), tab_nxt = tab_load(1);
+    request(0, tab_cur);
     for (int k = 0; k < nt; ++k)
     {
-        request(k + 1); // stage (k+1)&1 was released at the end of task k-1
+        request(k + 1, tab_nxt); // stage (k+1)&1 was released at the end of task k-1
         if (k + 1 >= nt) cp_async_commit(); // keep one group per iteration: wait_group<1> below
+        const int tab_nn = tab_load(k + 2); // in flight during this task
         int p, z0;
         task_of(k, p, z0);
         const int    b   = k & 1;
-        const int    lvl = __ldg(a.level + p);
+        const int    lvl = __shfl_sync(0xffffffffu, tab_cur, 24);
         const double cx = dt / a.dx[lvl][0], cy = dt / a.dx[lvl][1]; // amr_solver.hpp:330
         // CFL of the next step: speeds are state-independent (AdvectionPhysics.hpp:74-85), z has speed 0
         cand = fmin(cand, fmin(a.dx[lvl][0] / 1.0, a.dx[lvl][1] / 0.5));
@@ -233,6 +249,8 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
             *reinterpret_cast<double2*>(out + o) = r;
         }
         __syncwarp(); // every lane is done with stage b and ghost buffer b: task k+2 may overwrite them
+        tab_cur = tab_nxt;
+        tab_nxt = tab_nn;
     }
     cp_async_wait<0>();
 

@@ -101,10 +101,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // Value of ghost cell `idx` (padded multi-index, idx[dim] in the ghost range of direction d)
 // gathered from the neighbor patch(es) across face d.   field = base pointer of one field's
 // patch array.  nb = KF neighbor indices, meta = rel | quadrant bits << 2.
-template <int R, int S, int H, int HS = H>
+// neighbor indices of one (patch, direction) held in registers (kernels that prefetch their halo tables):
+// indexable like the table row, without a local-memory array
+template <int KF>
+struct NbRegs
+{
+    int32_t v[KF];
+    __device__ __forceinline__ int32_t operator[](int i) const
+    {
+        int32_t q = v[0];
+#pragma unroll
+        for (int k = 1; k < KF; ++k) q = (i == k) ? v[k] : q;
+        return q;
+    }
+};
+
+template <int R, int S, int H, int HS = H, typename NB = const int32_t*>
 __device__ __forceinline__ double
-halo_source(const double* __restrict__ field, const int32_t* __restrict__ nb, int meta, int d,
-            const int (&idx)[R])
+halo_source(const double* __restrict__ field, NB nb, int meta, int d, const int (&idx)[R])
 {
     using G        = Geo<R, S, H, HS>;
     const int dim  = d >> 1;

@@ -325,10 +325,14 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             F[2] = (fma(gc.u[2], uG, pGy) + fma(ic_.u[2], uI, pIy)) + sm * (gc.u[2] - ic_.u[2]);
             F[3] = (gc.u[3] * uG + ic_.u[3] * uI) + sm * (gc.u[3] - ic_.u[3]);
             F[4] = (uG * (gc.u[4] + gc.p) + uI * (ic_.u[4] + ic_.p)) + sm * (gc.u[4] - ic_.u[4]);
-            double2* o = reinterpret_cast<double2*>(sBF + ((z & 1) * 32 + lane) * C::BFW);
+            // parked as [buffer][chunk][face] double2: 16-byte slots of consecutive faces are consecutive in
+            // shared memory (the former face-major layout, 48 bytes per face, made lanes 0 / 8 / 16 / 24
+            // collide on every store and the two sides of a face pair on every load: 29 % of all shared
+            // wavefronts were conflict replays, profiles/r02c_euler3d_dense_ncu_summary.txt)
+            double2* o = reinterpret_cast<double2*>(sBF) + (z & 1) * 96 + lane;
             o[0]       = make_double2(F[0], F[1]);
-            o[1]       = make_double2(F[2], F[3]);
-            o[2]       = make_double2(F[4], 0.0);
+            o[32]      = make_double2(F[2], F[3]);
+            o[64]      = make_double2(F[4], 0.0);
         };
         // ghost cells of this lane's column pair across the z faces (d = 0 below, 1 above)
         auto zghost = [&](int d, double (&vA)[NV], double (&vB)[NV]) {
@@ -465,11 +469,11 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             flux3<2>(pv.A, nw.A, GzA);
             flux3<2>(pv.B, nw.B, GzB);
             finish(pv, GzA, GzB, fin);
-            const double* bfp = sBF + BUF * 32 * C::BFW;
+            const double2* bfp = reinterpret_cast<const double2*>(sBF) + BUF * 96;
             // ---- x faces
             {
-                const double2* bf = reinterpret_cast<const double2*>(bfp + ((xq >> 1) * 8 + yy) * C::BFW);
-                const double2  b0 = bf[0], b1 = bf[1], b2 = bf[2];
+                const double2* bf = bfp + ((xq >> 1) * 8 + yy);
+                const double2  b0 = bf[0], b1 = bf[32], b2 = bf[64];
                 const double   bfl[NV] = { b0.x, b0.y, b1.x, b1.y, b2.x };
                 Cell3          L;
 #pragma unroll
@@ -510,9 +514,8 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 double GyA[NV], GyB[NV];
                 flux3<1>(YA, nw.A, GyA);
                 flux3<1>(YB, nw.B, GyB);
-                const double2* bf =
-                    reinterpret_cast<const double2*>(bfp + ((2 + (yy >> 2)) * 8 + 2 * xq) * C::BFW);
-                const double2 c0 = bf[0], c1 = bf[1], c2 = bf[2], d0 = bf[3], d1 = bf[4], d2 = bf[5];
+                const double2* bf = bfp + ((2 + (yy >> 2)) * 8 + 2 * xq);
+                const double2  c0 = bf[0], c1 = bf[32], c2 = bf[64], d0 = bf[1], d1 = bf[33], d2 = bf[65];
                 const double  bA[NV] = { c0.x, c0.y, c1.x, c1.y, c2.x };
                 const double  bB[NV] = { d0.x, d0.y, d1.x, d1.y, d2.x };
 #pragma unroll

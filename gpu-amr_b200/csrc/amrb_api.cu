@@ -206,7 +206,9 @@ struct Inst
                 // warp-autonomous streaming kernel (amrb_advect2d.cuh).  variant 10 = thread per cell;
                 // 41 / 42 = 8- / 16-row bands of the streaming kernel for wide patches (default: patches
                 // wider than 16 cells keep the thread-per-cell kernel, narrower ones stream in groups)
-                const bool wide = (S > 16);
+                // measured (profiles/r02i_dev_bench.jsonl): 64-wide patches 0.59 thread per cell vs 0.57 streamed;
+                // 32-wide 0.37 vs 0.43 (16-row bands); narrower patches stream in groups (0.18 - 0.39 vs 0.09)
+                const bool wide = (S > 32);
                 if (a.variant != 10 && (!wide || a.variant == 41 || a.variant == 42))
                 {
                     auto launch = [&](auto kern, size_t smem, int tasks, int wpc, int ctas) {
@@ -215,7 +217,7 @@ struct Inst
                         const int grid = std::max(1, std::min(sm_count() * ctas, (tasks + wpc - 1) / wpc));
                         kern<<<grid, wpc * 32, smem, st>>>(a, n_items);
                     };
-                    if (wide && a.variant == 42)
+                    if ((wide && a.variant == 42) || (S == 32 && a.variant != 41))
                     {
                         using AC = Adv2Cfg<S, H, 4, (S % 16 == 0 ? 16 : 8)>;
                         launch(advect2d_kernel<S, H, 4, 2, (S % 16 == 0 ? 16 : 8)>, AC::SMEM, n_items * AC::NB, 4, 2);

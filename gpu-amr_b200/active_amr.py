@@ -26,12 +26,15 @@ class ActiveAmr:
     """single-GPU loop (DeviceTree) or sharded loop (ShardedSolver + global host tree), same interface"""
 
     def __init__(self, cfg, torch, device=0, dist=None, rank=0, world=1, p=C5, storage=B.STORAGE_INTERIOR,
-                 transport="p2p", host_ic=False):
+                 transport="p2p", host_ic=False, device_regrid=True):
         self.cfg, self.torch, self.device, self.p = cfg, torch, device, p
         self.host_ic = host_ic            # evaluate the pulse with numpy on the host (bit-comparable with the oracle)
         self.dist, self.rank, self.world = dist, rank, world
         self.storage, self.transport = storage, transport
         self.sharded = world > 1
+        # single GPU: the whole reconstruct (selection included) runs on the device, the host tree only mirrors
+        # the leaf ids; sharded meshes select on the host (every rank the same global flags)
+        self.device_regrid = device_regrid and not self.sharded
         self.updates = 0
         self.regrids = self.changed = 0
         host = B.HostTree(cfg.rank, cfg.depth)
@@ -103,6 +106,16 @@ class ActiveAmr:
         return self.pool.patch_max_flags(0, p["refine"], p["coarsen"], p["min_level"], p["max_level"])
 
     def regrid(self):
+        if self.device_regrid:
+            p = self.p
+            self.pool.flag_patches(0, p["refine"], p["coarsen"], p["min_level"], p["max_level"])
+            changed, _ = self.pool.reconstruct_device(None)
+            self.regrids += 1
+            if changed:
+                self.changed += 1
+                self.host.assign(self.pool.get_ids())
+                self.pool.halo_exchange()
+            return changed
         flags = self.flags()
         old_size = self.host.size
         changed = self.host.reconstruct(flags, self.p["capacity"])

@@ -120,6 +120,11 @@ def lib():
         "amrb_exchange_push": [vp, C.c_int, sz],
         "amrb_exchange_wait": [vp, C.c_int, sz],
         "amrb_pool_apply_plan": [vp, sz, i8p, i32p, i8p],
+        "amrb_pool_flag_patches": [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int],
+        "amrb_pool_reconstruct_device": [vp, vp, C.POINTER(C.c_int), C.POINTER(sz)],
+        "amrb_pool_get_ids": [vp, C.POINTER(C.c_uint64), sz],
+        "amrb_pool_get_plan": [vp, i8p, i32p, i8p],
+        "amrb_tree_assign": [vp, C.POINTER(C.c_uint64), sz],
         "amrb_pool_patch_max_flags": [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, i8p],
         "amrb_patch_max_flags_device": [vp, vp, sz, sz, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp],
         "amrb_profile_capture_start": [],
@@ -220,6 +225,11 @@ class HostTree:
         ch = C.c_int(0)
         check(self.L.amrb_tree_reconstruct(self.h, _ptr(flags), capacity, C.byref(ch)))
         return ch.value
+
+    def assign(self, ids):
+        """adopt a leaf set computed on the device (DevicePool.reconstruct_device)"""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        check(self.L.amrb_tree_assign(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint64)), len(ids)))
 
     def plan(self):
         n = self.L.amrb_tree_plan_size(self.h)
@@ -351,6 +361,27 @@ class DevicePool:
         check(self.L.amrb_pool_patch_max_flags(self.h, field, refine_thr, coarsen_thr, min_level,
                                                max_level, _ptr(out)))
         return out
+
+    def flag_patches(self, field, refine_thr, coarsen_thr, min_level, max_level):
+        """the criterion with the flags left on the device (no read-back)"""
+        check(self.L.amrb_pool_flag_patches(self.h, field, refine_thr, coarsen_thr, min_level, max_level))
+
+    def reconstruct_device(self, dev_flags=None):
+        """reconstruct_tree on the device: returns (changed, new size)"""
+        ch, n = C.c_int(0), C.c_size_t(0)
+        check(self.L.amrb_pool_reconstruct_device(self.h, C.c_void_p(dev_flags or 0), C.byref(ch), C.byref(n)))
+        return ch.value, n.value
+
+    def get_ids(self):
+        out = np.zeros(self.size, np.uint64)
+        check(self.L.amrb_pool_get_ids(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), len(out)))
+        return out
+
+    def get_plan(self):
+        n = self.size
+        kind, src, child = np.zeros(n, np.int8), np.zeros(n, np.int32), np.zeros(n, np.int8)
+        check(self.L.amrb_pool_get_plan(self.h, _ptr(kind), _ptr(src), _ptr(child)))
+        return kind, src, child
 
     def launch_count(self):
         return int(self.L.amrb_pool_launch_count(self.h))

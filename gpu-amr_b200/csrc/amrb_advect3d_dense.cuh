@@ -142,23 +142,17 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
             }
             else
             {
-                size_t o;
-                if (rel == 1)
-                    o = (size_t)nq * N + (size_t)z * SS + fy * S + fx; // same_t
-                else if (rel == 3)
-                {
-                    // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
-                    const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
-                    o = (size_t)nq * N + (size_t)(qz * HF + z / 2) * SS + (qy * HF + fy / 2) * S +
-                        (qx * HF + fx / 2);
-                }
-                else
-                {
-                    // relation "none" (never in a periodic balanced tree): the own boundary cell
-                    const int iy = (sd < 2) ? t : ((sd & 1) ? S - 1 : 0);
-                    const int ix = (sd < 2) ? ((sd & 1) ? S - 1 : 0) : t;
-                    o            = (size_t)p * N + (size_t)z * SS + iy * S + ix;
-                }
+                // same_t: the mirrored cell; coarser_t: injection of the covering coarse cell
+                // (patch_utils.hpp:315-332, 388-441); relation "none" (never in a periodic balanced tree): the
+                // own boundary cell.  One select per coordinate instead of a branch per relation.
+                const int  qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
+                const bool co = (rel == 3), none = (rel == 0);
+                const int  iy = (sd < 2) ? t : ((sd & 1) ? S - 1 : 0);
+                const int  ix = (sd < 2) ? ((sd & 1) ? S - 1 : 0) : t;
+                const int  sz = co ? qz * HF + z / 2 : z;
+                const int  sy = co ? qy * HF + fy / 2 : (none ? iy : fy);
+                const int  sx = co ? qx * HF + fx / 2 : (none ? ix : fx);
+                const size_t o = (size_t)(none ? p : nq) * N + (size_t)sz * SS + sy * S + sx;
                 cp_async8(gdst + e, cur + o);
             }
         }
@@ -194,21 +188,23 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
         const double* pl = ring + b * C::TASK;
         const double* gh = sG + b * GH;
         double*       out = nxt + (size_t)p * N + (size_t)z0 * SS;
-#pragma unroll 4
+        // branch-free loop body: the ghost cells are ALWAYS loaded (valid addresses for every lane) and merged
+        // with selects, the y-neighbors come through a selected pointer -- the divergent if / else regions of the
+        // first version were 23 % of all issued instructions (profiles/r02i_advect3d_dense_ncu_summary.txt)
+#pragma unroll
         for (int it = 0; it < C::TASK / 64; ++it)
         {
             const int q  = it * 32 + lane; // pair index inside the task
             const int x2 = q % HP, y = (q / HP) % S, zl = q / (HP * S);
             const int o  = zl * SS + y * S + 2 * x2;
             const double2 c = *reinterpret_cast<const double2*>(pl + o);
-            double        lft = __shfl_up_sync(0xffffffffu, c.y, 1);
-            double        rgt = __shfl_down_sync(0xffffffffu, c.x, 1);
-            if (x2 == 0) lft = gh[(0 * ZT + zl) * S + y];
-            if (x2 == HP - 1) rgt = gh[(1 * ZT + zl) * S + y];
-            const double2 dn = (y > 0) ? *reinterpret_cast<const double2*>(pl + o - S)
-                                       : *reinterpret_cast<const double2*>(gh + (2 * ZT + zl) * S + 2 * x2);
-            const double2 up = (y < S - 1) ? *reinterpret_cast<const double2*>(pl + o + S)
-                                           : *reinterpret_cast<const double2*>(gh + (3 * ZT + zl) * S + 2 * x2);
+            const double  gl = gh[(0 * ZT + zl) * S + y], gr = gh[(1 * ZT + zl) * S + y];
+            const double  sl = __shfl_up_sync(0xffffffffu, c.y, 1), sr = __shfl_down_sync(0xffffffffu, c.x, 1);
+            const double  lft = (x2 == 0) ? gl : sl, rgt = (x2 == HP - 1) ? gr : sr;
+            const double* pdn = (y > 0) ? pl + o - S : gh + (2 * ZT + zl) * S + 2 * x2;
+            const double* pup = (y < S - 1) ? pl + o + S : gh + (3 * ZT + zl) * S + 2 * x2;
+            const double2 dn = *reinterpret_cast<const double2*>(pdn);
+            const double2 up = *reinterpret_cast<const double2*>(pup);
             double2 r;
             {
                 // cell A: left = lft, right = c.y

@@ -665,6 +665,7 @@ amrb_status amrb_pool_destroy(amrb_pool* p)
     if (!p) return AMRB_OK;
     cudaSetDevice(p->device);
     if (p->stream || !p->own_stream) cudaStreamSynchronize(p->stream);
+    regrid_release(p);
     if (p->own_mem)
         for (int f = 0; f < kMaxVar; ++f)
         {
@@ -1367,6 +1368,31 @@ amrb_status amrb_pool_patch_max_flags(amrb_pool* p, int field, double refine_thr
     AMRB_CUDA(cudaMemcpyAsync(flags, p->d_flags, p->n_owned, cudaMemcpyDeviceToHost, p->stream));
     AMRB_CUDA(cudaStreamSynchronize(p->stream));
     return AMRB_OK;
+}
+
+// the same criterion, flags left on the device (input of amrb_pool_reconstruct_device); asynchronous
+amrb_status amrb_pool_flag_patches(amrb_pool* p, int field, double refine_threshold, double coarsen_threshold,
+                                   int min_level, int max_level)
+{
+    if (!p) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    if (field < 0 || field >= p->lay.nvar) return fail(AMRB_ERR_ARGUMENT, "field out of range");
+    AMRB_TRY(need_topology(p));
+    AMRB_TRY(set_device(p));
+    AMRB_TRY(amrb_pool_ensure_halos(p));
+    if (p->flags_cap < p->n_owned)
+    {
+        cudaFree(p->d_flags);
+        p->flags_cap = 0;
+        AMRB_CUDA(cudaMalloc(&p->d_flags, p->n_owned * 2));
+        p->flags_cap = p->n_owned * 2;
+    }
+    if (p->dense)
+        p->ops->flags_dense(p->stream, p->cur.p[field], p->d_nbr, p->d_meta, p->d_level, (int)p->n_owned,
+                            refine_threshold, coarsen_threshold, min_level, max_level, p->d_flags);
+    else
+        p->ops->flags(p->stream, p->cur.p[field], p->d_level, (int)p->n_owned, refine_threshold,
+                      coarsen_threshold, min_level, max_level, p->d_flags);
+    return check_launch(p, "patch_max_flags_kernel");
 }
 
 amrb_status amrb_patch_max_flags_device(const double* dev_field, const int32_t* dev_levels,

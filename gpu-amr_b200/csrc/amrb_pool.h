@@ -54,6 +54,8 @@ namespace amrb
 {
 // status + message of the calling thread (amrb_last_error)
 amrb_status fail(amrb_status code, const std::string& what);
+// scratch of the device reconstruct (amrb_regrid.cu), released with the pool
+void regrid_release(amrb_pool* p);
 } // namespace amrb
 
 #define AMRB_CUDA(expr)                                                                          \

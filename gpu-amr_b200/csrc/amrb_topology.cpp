@@ -447,6 +447,20 @@ amrb_status amrb_tree_reconstruct(amrb_tree* t, const int8_t* flags, size_t capa
     return AMRB_OK;
 }
 
+// adopt a leaf set computed elsewhere (amrb_pool_reconstruct_device): ascending ids
+amrb_status amrb_tree_assign(amrb_tree* t, const uint64_t* ids, size_t n)
+{
+    if (!t || !ids || n == 0) return tfail(AMRB_ERR_ARGUMENT, "null argument");
+    for (size_t i = 1; i < n; ++i)
+        if (!(ids[i - 1] < ids[i])) return tfail(AMRB_ERR_ARGUMENT, "leaf ids must be strictly ascending");
+    t->ids.assign(ids, ids + n);
+    t->invalidate_map();
+    t->plan_kind.clear();
+    t->plan_src.clear();
+    t->plan_child.clear();
+    return AMRB_OK;
+}
+
 size_t amrb_tree_plan_size(const amrb_tree* t) { return t ? t->plan_kind.size() : 0; }
 
 amrb_status amrb_tree_plan(const amrb_tree* t, int8_t* kind, int32_t* src, int8_t* child)

@@ -323,6 +323,24 @@ amrb_status amrb_pool_patch_max_flags(amrb_pool* pool, int field, double refine_
                                       double coarsen_threshold, int min_level, int max_level,
                                       int8_t* flags);
 
+/* the same criterion with the flags LEFT ON THE DEVICE (no read-back; input of amrb_pool_reconstruct_device) */
+amrb_status amrb_pool_flag_patches(amrb_pool* pool, int field, double refine_threshold,
+                                   double coarsen_threshold, int min_level, int max_level);
+/* reconstruct_tree on the device (replaces the host side of ndtree.hpp:886-940, 1127-1271):
+ * selection (eligibility, 2:1 ripple, coarsening veto) over the device halo tables, new leaf ids in Morton
+ * order, transfer plan, data motion and new halo tables -- the leaf set and the flags never leave the GPU; the
+ * host reads back two integers.  dev_flags: device array [size] of AMRB_{STABLE,REFINE,COARSEN} (NULL = the
+ * flags of the last amrb_pool_flag_patches).  Needs the topology built by amrb_pool_set_topology_from_ids
+ * (single GPU, no ghost slots).  Bit-identical to amrb_tree_reconstruct + amrb_pool_apply_plan +
+ * amrb_pool_set_topology_from_ids.  Blocking (one 8-byte read-back). */
+amrb_status amrb_pool_reconstruct_device(amrb_pool* pool, const int8_t* dev_flags, int* changed,
+                                         size_t* new_size);
+/* leaf ids of the device topology (ascending), to mirror a device reconstruct into an amrb_tree */
+amrb_status amrb_pool_get_ids(amrb_pool* pool, uint64_t* host_ids, size_t capacity);
+amrb_status amrb_tree_assign(amrb_tree* tree, const uint64_t* ids, size_t n);
+/* transfer plan of the last device reconstruct: kind / src / child per new leaf (tests) */
+amrb_status amrb_pool_get_plan(amrb_pool* pool, int8_t* kind, int32_t* src, int8_t* child);
+
 /* raw-pointer form of the same criterion — replaces
  * amr::cuda::compute_scalar_patch_amr_decisions_from_device
  * (include/cuda/fvm_refinement_criterion.hpp:20-27): all pointers are device pointers,

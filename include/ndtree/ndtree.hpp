@@ -352,7 +352,24 @@ public:
         m_status.assign(size(), 0);
         if constexpr (requires(Fn& f, ndtree& t) { f.fill_refine_flags(t); })
         {
+            // the criterion writes its decisions into the device refine-status buffer
+            // (compute_scalar_patch_amr_decisions_from_device): the whole reconstruct -- selection, 2:1 ripple,
+            // coarsening veto, data motion, new tables -- stays on the device, the host mirrors the leaf ids
             fn.fill_refine_flags(*this);
+            make_device_current();
+            int         changed = 0;
+            std::size_t n_new   = 0;
+            check(amrb_pool_reconstruct_device(m_pool, m_device_refine_status, &changed, &n_new), "reconstruct_tree");
+            if (!changed) return;
+            std::vector<std::uint64_t> raw(n_new);
+            check(amrb_pool_get_ids(m_pool, raw.data(), n_new), "amrb_pool_get_ids");
+            check(amrb_tree_assign(m_topo, raw.data(), n_new), "amrb_tree_assign");
+            m_ids.resize(n_new);
+            for (size_type i = 0; i != n_new; ++i) m_ids[i] = patch_index_t{ raw[i] };
+            m_status.assign(n_new, 0);
+            m_host_tables_valid = false;
+            m_device_newer      = true;
+            return;
         }
         else
         {

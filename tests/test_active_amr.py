@@ -23,15 +23,16 @@ def _oracle_flags(tree, cfg, p):
     return f
 
 
+@pytest.mark.parametrize("device_regrid", [True, False], ids=["device_selection", "host_selection"])
 @pytest.mark.parametrize("storage", [1, 0], ids=["interior", "padded"])
-def test_active_amr_3d_advection_matches_oracle(amrb, storage):
+def test_active_amr_3d_advection_matches_oracle(amrb, storage, device_regrid):
     import torch
 
     aa = importlib.import_module("gpu-amr_b200.active_amr")
     wl = importlib.import_module("gpu-amr_b200.workloads")
     p = dict(aa.C5, depth=5, min_level=2, max_level=4, capacity=6000)
     cfg = wl.Config(3, 8, 1, p["depth"], amrb.EQ_ADVECTION)
-    run = aa.ActiveAmr(cfg, torch, p=p, storage=storage, host_ic=True)
+    run = aa.ActiveAmr(cfg, torch, p=p, storage=storage, host_ic=True, device_regrid=device_regrid)
 
     ocfg = O.Config.from_name("r3_s8_h1_d5_adv")
     orc = O.OracleTree(ocfg, capacity=6000)

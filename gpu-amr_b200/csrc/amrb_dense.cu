@@ -33,6 +33,17 @@ struct DenseInst
         const int grid  = std::max(1, std::min(device_sm_count() * MINB, (tasks + WPC - 1) / WPC));
         k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
     }
+    template <int CR, int NS, int WPC, int MINB>
+    static void march_pp(cudaStream_t st, const StepArgs& a, int n_items)
+    {
+        using MC = March3DenseCfg<S, CR, NS, WPC>;
+        auto k   = euler3d_dense_kernel_pp<S, CR, NS, WPC, MINB>;
+        static DevicePrepared prepared;
+        if (!prepared.ensure((const void*)k, (int)MC::SMEM)) return;
+        const int tasks = n_items * MC::NB;
+        const int grid  = std::max(1, std::min(device_sm_count() * MINB, (tasks + WPC - 1) / WPC));
+        k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
+    }
     template <int CR, int NS, int WPC, int MAXREG, int CTAS>
     static void march_r(cudaStream_t st, const StepArgs& a, int n_items)
     {
@@ -69,6 +80,8 @@ struct DenseInst
                     march<2, 3, 4, 2>(st, a, n_items);
                 else if (a.variant == 22)
                     march<2, 2, 4, 3>(st, a, n_items);
+                else if (a.variant == 28)
+                    march_pp<4, 2, 4, 2>(st, a, n_items); // two planes per loop trip, no state copies
                 else if (a.variant == 25)
                     march_r<2, 3, 5, 200, 2>(st, a, n_items); // 10 warps per SM, 200 registers
                 else if (a.variant == 26)

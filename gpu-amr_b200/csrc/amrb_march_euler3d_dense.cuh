@@ -47,7 +47,7 @@ struct March3DenseCfg
     static_assert((FS * 8) % 16 == 0 && (WARP_DOUBLES * 8) % 16 == 0, "bulk copy alignment");
 };
 
-template <int S, int CR, int NS, int WPC>
+template <int S, int CR, int NS, int WPC, bool PINGPONG = false>
 __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_items)
 {
     using C           = March3DenseCfg<S, CR, NS, WPC>;
@@ -581,16 +581,35 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
         }
         prims3(s0.A, g, gm1);
         prims3(s0.B, g, gm1);
-#pragma unroll 1
-        for (int z = 0; z < S; ++z)
+        if constexpr (PINGPONG)
         {
-            if (z == 2)
+            // two planes per trip, the two plane states swapping roles: no copy of the 26 carried doubles per
+            // plane (6 % of the issued instructions were those moves), at twice the loop body
+#pragma unroll 1
+            for (int z = 0; z < S; z += 2)
             {
-                resolve_next(); // the next task is known by now: request its halo tables
-                if (tau_nxt < n_tasks) tab_nxt = tab_load(tau_nxt);
+                if (z == 2)
+                {
+                    resolve_next();
+                    if (tau_nxt < n_tasks) tab_nxt = tab_load(tau_nxt);
+                }
+                plane_step(z, s0, s1, z > 0, false);
+                plane_step(z + 1, s1, s0, true, z + 1 == S - 1);
             }
-            plane_step(z, s0, s1, z > 0, z == S - 1);
-            s0 = s1;
+        }
+        else
+        {
+#pragma unroll 1
+            for (int z = 0; z < S; ++z)
+            {
+                if (z == 2)
+                {
+                    resolve_next(); // the next task is known by now: request its halo tables
+                    if (tau_nxt < n_tasks) tab_nxt = tab_load(tau_nxt);
+                }
+                plane_step(z, s0, s1, z > 0, z == S - 1);
+                s0 = s1;
+            }
         }
         // ghost plane above: z-face flux into plane S-1, finish it
         {
@@ -635,6 +654,13 @@ __global__ void __launch_bounds__(WPC * 32, MINB)
 euler3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
 {
     euler3d_dense_body<S, CR, NS, WPC>(a, n_items);
+}
+// two planes per loop trip (ping-pong plane states)
+template <int S, int CR, int NS, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+euler3d_dense_kernel_pp(const __grid_constant__ StepArgs a, int n_items)
+{
+    euler3d_dense_body<S, CR, NS, WPC, true>(a, n_items);
 }
 // occupancy by an explicit register budget (CTA sizes that are not multiples of 128 threads)
 template <int S, int CR, int NS, int WPC, int MAXREG>

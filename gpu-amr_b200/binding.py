@@ -116,7 +116,8 @@ def lib():
         "amrb_ipc_close": [vp],
         "amrb_exchange_connect": [vp, C.c_int, vp, vp, vp],
         "amrb_exchange_halo": [vp],
-        "amrb_exchange_advance_batch_async": [vp, sz, C.c_double],
+        "amrb_exchange_advance_batch_async": [vp, sz, C.c_double, C.c_int],
+        "amrb_exchange_set_lists": [vp, i32p, sz, i32p, sz],
         "amrb_exchange_push": [vp, C.c_int, sz],
         "amrb_exchange_wait": [vp, C.c_int, sz],
         "amrb_pool_apply_plan": [vp, sz, i8p, i32p, i8p],

@@ -28,8 +28,9 @@ constexpr int kMaxWorld = 8;
 
 struct Mailbox // device memory of the RECEIVING rank, written by its peers
 {
-    unsigned long long flag[kMaxWorld];     // flag[r] = last generation rank r has pushed here
-    unsigned long long dtmin[2][kMaxWorld]; // bits of rank r's local dt-min, by generation parity
+    unsigned long long flag[kMaxWorld];     // flag[r]  = last DATA generation rank r has pushed here
+    unsigned long long tflag[kMaxWorld];    // tflag[r] = last CFL-minimum generation rank r has delivered
+    unsigned long long dtmin[2][kMaxWorld]; // bits of rank r's local dt-min, by dt-generation parity
 };
 
 struct PushArgs
@@ -43,7 +44,8 @@ struct PushArgs
     Mailbox*                  peer_box[kMaxWorld];      // peer r's mailbox (nullptr: not connected / self)
     unsigned int*             done;       // CTA completion counter (this rank)
     const unsigned long long* my_dtmin;   // this rank's dt-min slot of the step about to run (may be null)
-    unsigned long long        gen;
+    unsigned long long        gen;        // data generation of this push (0: no slabs, CFL minimum only)
+    unsigned long long        tgen;       // dt generation (0: no CFL minimum in this push)
     int                       R, S, HS, NV, T, stored; // geometry: rank, size, stored halo, fields, layers, doubles per field-patch
 };
 
@@ -105,8 +107,12 @@ __global__ void __launch_bounds__(128) face_push_kernel(const __grid_constant__ 
     if (threadIdx.x < a.world && threadIdx.x != a.rank && a.peer_box[threadIdx.x] != nullptr)
     {
         Mailbox* box = a.peer_box[threadIdx.x];
-        if (a.my_dtmin != nullptr) box->dtmin[a.gen & 1][a.rank] = *a.my_dtmin;
-        st_release_sys(&box->flag[a.rank], a.gen);
+        if (a.tgen != 0)
+        {
+            box->dtmin[a.tgen & 1][a.rank] = *a.my_dtmin;
+            st_release_sys(&box->tflag[a.rank], a.tgen);
+        }
+        if (a.gen != 0) st_release_sys(&box->flag[a.rank], a.gen);
     }
     if (threadIdx.x == 0) *a.done = 0u; // ready for the next launch (stream-ordered)
 }
@@ -114,7 +120,8 @@ __global__ void __launch_bounds__(128) face_push_kernel(const __grid_constant__ 
 // one warp: lane r waits for rank r's push of generation `gen`, then the warp folds the peers' dt-minima
 // into this rank's slot (bit patterns of positive doubles order like unsigned integers)
 __global__ void exchange_wait_kernel(Mailbox* box, int world, int rank, unsigned long long gen,
-                                     unsigned long long* my_dtmin, int* timed_out, long long timeout_cycles)
+                                     unsigned long long tgen, unsigned long long* my_dtmin, int* timed_out,
+                                     long long timeout_cycles)
 {
     const int          lane = threadIdx.x;
     unsigned long long v    = ~0ull;
@@ -122,7 +129,7 @@ __global__ void exchange_wait_kernel(Mailbox* box, int world, int rank, unsigned
     {
         const long long t0 = clock64();
         bool            ok = true;
-        while (ld_acquire_sys(&box->flag[lane]) < gen)
+        while (ld_acquire_sys(&box->flag[lane]) < gen || ld_acquire_sys(&box->tflag[lane]) < tgen)
         {
             if (clock64() - t0 > timeout_cycles)
             {
@@ -134,7 +141,7 @@ __global__ void exchange_wait_kernel(Mailbox* box, int world, int rank, unsigned
         if (!ok)
             atomicExch(timed_out, 1);
         else if (my_dtmin != nullptr)
-            v = box->dtmin[gen & 1][lane];
+            v = box->dtmin[tgen & 1][lane];
     }
     else if (lane == rank && my_dtmin != nullptr)
         v = *my_dtmin;
@@ -164,21 +171,30 @@ struct amrb_exchange
     size_t       seg_offset[kMaxWorld] = {}; // where my segment starts inside peer r's receive buffer [doubles]
     Mailbox*     peer_box[kMaxWorld] = {};
     double*      peer_recv[kMaxWorld][2] = {};
-    unsigned long long gen = 0;
+    unsigned long long gen = 0;             // data generation (slab pushes)
+    unsigned long long tgen = 0;            // dt generation (CFL minima delivered)
+    int32_t*     d_boundary = nullptr;      // owned patches with a remote neighbor / without (overlap schedule)
+    int32_t*     d_interior = nullptr;
+    size_t       n_boundary = 0, n_interior = 0;
+    cudaStream_t side = nullptr;            // the slab push of step k+1 runs here, under the interior launch of step k
+    cudaEvent_t  ev_boundary = nullptr, ev_push = nullptr;
     int          slab_doubles = 0;          // per entry, all fields
     uint64_t     launches = 0;
 };
 
 namespace
 {
-amrb_status push(amrb_exchange* ex, const unsigned long long* dtmin_slot)
+// one push: the slabs of `src` (data = true) and / or this rank's CFL minimum (dtmin_slot != null) + flags
+amrb_status push(amrb_exchange* ex, const unsigned long long* dtmin_slot, bool data = true,
+                 const FieldPtrs* src = nullptr, cudaStream_t stream = nullptr)
 {
     amrb_pool* p = ex->pool;
-    ++ex->gen;
+    if (data) ++ex->gen;
+    if (dtmin_slot) ++ex->tgen;
     PushArgs a{};
-    a.cur     = p->cur;
+    a.cur     = src ? *src : p->cur;
     a.entries = ex->d_send;
-    a.count   = (int)ex->n_send;
+    a.count   = data ? (int)ex->n_send : 0;
     a.world   = ex->world;
     a.rank    = ex->rank;
     std::memcpy(a.seg_start, ex->seg_start, sizeof(a.seg_start));
@@ -187,16 +203,17 @@ amrb_status push(amrb_exchange* ex, const unsigned long long* dtmin_slot)
         a.peer_box[r]  = (r == ex->rank) ? nullptr : ex->peer_box[r];
         a.peer_recv[r] = ex->peer_recv[r][ex->gen & 1] ? ex->peer_recv[r][ex->gen & 1] + ex->seg_offset[r] : nullptr;
     }
-    a.done     = ex->d_done;
+    a.done     = data ? ex->d_done : ex->d_done + 1; // the two kinds of push may overlap: separate counters
     a.my_dtmin = dtmin_slot;
-    a.gen      = ex->gen;
+    a.gen      = data ? ex->gen : 0;
+    a.tgen     = dtmin_slot ? ex->tgen : 0;
     a.R        = p->lay.rank;
     a.S        = p->lay.size[0];
     a.HS       = p->dense ? 0 : p->lay.halo;
     a.NV       = p->lay.nvar;
     a.T        = std::min(2 * p->lay.halo, p->lay.size[0]);
     a.stored   = (int)p->flat;
-    face_push_kernel<<<(unsigned)std::max<size_t>(ex->n_send, 1), 128, 0, p->stream>>>(a);
+    face_push_kernel<<<(unsigned)std::max<size_t>(a.count, 1), 128, 0, stream ? stream : p->stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("face_push_kernel: ") + cudaGetErrorString(e));
     ++ex->launches;
@@ -207,8 +224,8 @@ amrb_status wait_and_unpack(amrb_exchange* ex, unsigned long long* dtmin_slot)
 {
     amrb_pool* p = ex->pool;
     // ~4 s at 2 GHz: a peer that died must not hang this GPU
-    exchange_wait_kernel<<<1, 32, 0, p->stream>>>(ex->box, ex->world, ex->rank, ex->gen, dtmin_slot, ex->h_timeout,
-                                                  8000000000ll);
+    exchange_wait_kernel<<<1, 32, 0, p->stream>>>(ex->box, ex->world, ex->rank, ex->gen, ex->tgen, dtmin_slot,
+                                                  ex->h_timeout, 8000000000ll);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("exchange_wait_kernel: ") + cudaGetErrorString(e));
     ++ex->launches;
@@ -264,8 +281,8 @@ amrb_status amrb_exchange_create(amrb_pool* pool, int rank, int world, const int
         AMRB_CUDA(cudaMalloc(&ex->recv[b], ex->recv_doubles * sizeof(double)));
         AMRB_CUDA(cudaMemset(ex->recv[b], 0, ex->recv_doubles * sizeof(double)));
     }
-    AMRB_CUDA(cudaMalloc(&ex->d_done, sizeof(unsigned int)));
-    AMRB_CUDA(cudaMemset(ex->d_done, 0, sizeof(unsigned int)));
+    AMRB_CUDA(cudaMalloc(&ex->d_done, 2 * sizeof(unsigned int)));
+    AMRB_CUDA(cudaMemset(ex->d_done, 0, 2 * sizeof(unsigned int)));
     AMRB_CUDA(cudaHostAlloc(&ex->h_timeout, sizeof(int), cudaHostAllocMapped));
     *ex->h_timeout = 0;
     if (n_send)
@@ -294,6 +311,11 @@ amrb_status amrb_exchange_destroy(amrb_exchange* ex)
     cudaFree(ex->d_done);
     cudaFree(ex->d_send);
     cudaFree(ex->d_recv);
+    cudaFree(ex->d_boundary);
+    cudaFree(ex->d_interior);
+    if (ex->side) cudaStreamDestroy(ex->side);
+    if (ex->ev_boundary) cudaEventDestroy(ex->ev_boundary);
+    if (ex->ev_push) cudaEventDestroy(ex->ev_push);
     if (ex->h_timeout) cudaFreeHost(ex->h_timeout);
     cudaGetLastError();
     delete ex;
@@ -352,19 +374,90 @@ amrb_status amrb_exchange_halo(amrb_exchange* ex)
 
 // amr_solver::advance_batch_async (solver/amr_solver.hpp:155-243) over the sharded mesh: per step one
 // push (slabs + CFL minimum + flag), one wait (+ all-reduce(min) fold), the local unpack, the fused step.
-amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, double remaining)
+// owned patches with / without a remote neighbor (ShardPlan.boundary / .interior): enables the overlapped
+// schedule of amrb_exchange_advance_batch_async
+amrb_status amrb_exchange_set_lists(amrb_exchange* ex, const int32_t* boundary, size_t n_boundary,
+                                    const int32_t* interior, size_t n_interior)
+{
+    if (!ex || (n_boundary && !boundary) || (n_interior && !interior)) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    AMRB_CUDA(cudaSetDevice(ex->pool->device));
+    AMRB_CUDA(cudaStreamSynchronize(ex->pool->stream));
+    cudaFree(ex->d_boundary);
+    cudaFree(ex->d_interior);
+    ex->d_boundary = ex->d_interior = nullptr;
+    ex->n_boundary = n_boundary;
+    ex->n_interior = n_interior;
+    if (n_boundary)
+    {
+        AMRB_CUDA(cudaMalloc(&ex->d_boundary, n_boundary * sizeof(int32_t)));
+        AMRB_CUDA(cudaMemcpy(ex->d_boundary, boundary, n_boundary * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (n_interior)
+    {
+        AMRB_CUDA(cudaMalloc(&ex->d_interior, n_interior * sizeof(int32_t)));
+        AMRB_CUDA(cudaMemcpy(ex->d_interior, interior, n_interior * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (!ex->side)
+    {
+        AMRB_CUDA(cudaStreamCreateWithFlags(&ex->side, cudaStreamNonBlocking));
+        AMRB_CUDA(cudaEventCreateWithFlags(&ex->ev_boundary, cudaEventDisableTiming));
+        AMRB_CUDA(cudaEventCreateWithFlags(&ex->ev_push, cudaEventDisableTiming));
+    }
+    return AMRB_OK;
+}
+
+// amr_solver::advance_batch_async (solver/amr_solver.hpp:155-243) over the sharded mesh.
+//   plain schedule (overlap = 0):  per step push (slabs + CFL minimum + flags), wait (+ all-reduce(min) fold),
+//       unpack, the fused step over all owned patches;
+//   overlapped schedule (overlap = 1, needs amrb_exchange_set_lists): per step wait + unpack, the fused step over
+//       the BOUNDARY patches, then -- on a side stream, under the launch over the INTERIOR patches -- the slab push
+//       of the next step straight from the next buffer; the CFL minimum follows in a push of its own once both
+//       launches are done.  The NVLink transfer hides behind the interior launch; pays when a rank's share is
+//       large (C3: ~250 000 patches per rank), costs two launches per step when it is small.
+amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, double remaining, int overlap)
 {
     if (!ex) return fail(AMRB_ERR_ARGUMENT, "null exchange");
     amrb_pool* p = ex->pool;
+    const bool ov = overlap && ex->side && ex->n_boundary > 0 && ex->n_interior > 0 && steps > 0;
     AMRB_TRY(amrb_pool_batch_begin(p, steps, remaining));
     amrb_status s = AMRB_OK;
-    for (size_t k = 0; k < steps && s == AMRB_OK; ++k)
+    auto slot = [&](size_t k) { return reinterpret_cast<unsigned long long*>(amrb_pool_dtmin_slot(p, k)); };
+    if (!ov)
     {
-        unsigned long long* slot = reinterpret_cast<unsigned long long*>(amrb_pool_dtmin_slot(p, k));
-        s = push(ex, slot);
-        if (s == AMRB_OK) s = wait_and_unpack(ex, slot);
-        if (s == AMRB_OK) s = amrb_pool_step_partial(p, nullptr, 0);
-        if (s == AMRB_OK) s = amrb_pool_step_commit(p);
+        for (size_t k = 0; k < steps && s == AMRB_OK; ++k)
+        {
+            s = push(ex, slot(k));
+            if (s == AMRB_OK) s = wait_and_unpack(ex, slot(k));
+            if (s == AMRB_OK) s = amrb_pool_step_partial(p, nullptr, 0);
+            if (s == AMRB_OK) s = amrb_pool_step_commit(p);
+        }
+    }
+    else
+    {
+        s = push(ex, slot(0)); // the first exchange has nothing to hide behind
+        for (size_t k = 0; k < steps && s == AMRB_OK; ++k)
+        {
+            s = wait_and_unpack(ex, slot(k));
+            // the slab push of the previous step read the buffer this step writes two steps later: done by now
+            if (s == AMRB_OK && k > 0 && cudaStreamWaitEvent(p->stream, ex->ev_push, 0) != cudaSuccess)
+                s = fail(AMRB_ERR_CUDA, "cudaStreamWaitEvent");
+            if (s == AMRB_OK) s = amrb_pool_step_partial(p, ex->d_boundary, ex->n_boundary);
+            if (s == AMRB_OK && k + 1 < steps)
+            {
+                // boundary patches of the new state are in the NEXT buffer: push them while the interior runs
+                if (cudaEventRecord(ex->ev_boundary, p->stream) != cudaSuccess ||
+                    cudaStreamWaitEvent(ex->side, ex->ev_boundary, 0) != cudaSuccess)
+                    s = fail(AMRB_ERR_CUDA, "cudaEventRecord / cudaStreamWaitEvent");
+                if (s == AMRB_OK) s = push(ex, nullptr, true, &p->nxt, ex->side);
+                if (s == AMRB_OK && cudaEventRecord(ex->ev_push, ex->side) != cudaSuccess)
+                    s = fail(AMRB_ERR_CUDA, "cudaEventRecord");
+            }
+            if (s == AMRB_OK) s = amrb_pool_step_partial(p, ex->d_interior, ex->n_interior);
+            if (s == AMRB_OK && k + 1 < steps) s = push(ex, slot(k + 1), false); // CFL minimum of the new state
+            if (s == AMRB_OK) s = amrb_pool_step_commit(p);
+        }
+        if (s == AMRB_OK && steps > 1 && cudaStreamWaitEvent(p->stream, ex->ev_push, 0) != cudaSuccess)
+            s = fail(AMRB_ERR_CUDA, "cudaStreamWaitEvent");
     }
     if (s == AMRB_OK) s = push(ex, nullptr);
     if (s == AMRB_OK) s = wait_and_unpack(ex, nullptr);

@@ -222,6 +222,9 @@ class ShardedSolver:
         B.check(L.amrb_exchange_create(self.pool.h, self.rank, self.world, B._ptr(se), B._ptr(sc), B._ptr(so),
                                        B._ptr(re), len(re), C.byref(ex)))
         self.ex = ex
+        bd = np.ascontiguousarray(pl.boundary, np.int32)
+        it = np.ascontiguousarray(pl.interior, np.int32)
+        B.check(L.amrb_exchange_set_lists(ex, B._ptr(bd), len(bd), B._ptr(it), len(it)))
         if self.dist is None:
             return                       # in-process cluster: LocalCluster connects the raw pointers
         handles = []
@@ -397,7 +400,7 @@ class ShardedSolver:
         L, h, pl = self.L, self.pool.h, self.plan
         if self.ex is not None:
             l0 = int(L.amrb_exchange_launch_count(self.ex)) + self.pool.launch_count()
-            B.check(L.amrb_exchange_advance_batch_async(self.ex, steps, remaining))
+            B.check(L.amrb_exchange_advance_batch_async(self.ex, steps, remaining, 1 if overlap else 0))
             self.launches += int(L.amrb_exchange_launch_count(self.ex)) + self.pool.launch_count() - l0
             return
         B.check(L.amrb_pool_batch_begin(h, steps, remaining))

@@ -272,7 +272,12 @@ amrb_status amrb_exchange_connect(amrb_exchange* ex, int peer, void* mailbox, vo
 amrb_status amrb_exchange_halo(amrb_exchange* ex);
 /* amrb_pool_advance_batch_async over the sharded mesh: per step push + wait/fold + unpack + fused step;
  * ends with an exchange and the halo materialisation.  Read back with amrb_pool_finish_advance_batch. */
-amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, double remaining_time);
+amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, double remaining_time,
+                                              int overlap);
+/* owned patches with / without a remote neighbor: with them, overlap = 1 above runs the boundary patches first
+ * and pushes their slabs from the next buffer on a side stream while the interior patches are advanced */
+amrb_status amrb_exchange_set_lists(amrb_exchange* ex, const int32_t* boundary, size_t n_boundary,
+                                    const int32_t* interior, size_t n_interior);
 /* the two halves of one exchange (drivers that interleave several ranks in one process); with_dt folds the
  * CFL minimum of slot k of the open batch */
 amrb_status amrb_exchange_push(amrb_exchange* ex, int with_dt, size_t k);

@@ -873,9 +873,12 @@ def run_bench(args, METRIC, UNIT):
                        "transport": "peer-memory push over NVLink (slabs + CFL minimum + flag in one kernel), "
                                     "K-step loop in the library" if sol.transport == "p2p" else
                                     "NCCL all_to_all_single + all_reduce(min) driven from Python",
-                       "exchange_schedule": "push, wait, unpack, one launch over all patches" if sol.transport == "p2p"
-                       else ("interior patches overlap the slab exchange" if overlap else
-                             "exchange, then one launch over all patches"),
+                       "exchange_schedule": (("boundary patches first, slab push of the next step on a side stream under "
+                                              "the interior launch" if overlap else
+                                              "push, wait, unpack, one launch over all patches")
+                                             if sol.transport == "p2p" else
+                                             ("interior patches overlap the slab exchange" if overlap else
+                                              "exchange, then one launch over all patches")),
                        "schedule_probe_ms_per_6_steps": {"overlap": mode_ms[True], "single_launch": mode_ms[False]},
                        "ghost_patches_max_rank": int(mx[2].item()), "boundary_patches_max_rank": int(mx[3].item()),
                        "ghost_bytes_per_step_all_ranks": float(tot[1].item())})

@@ -118,6 +118,8 @@ def lib():
         "amrb_exchange_halo": [vp],
         "amrb_exchange_advance_batch_async": [vp, sz, C.c_double, C.c_int],
         "amrb_exchange_set_lists": [vp, i32p, sz, i32p, sz],
+        "amrb_exchange_set_timing": [vp, C.c_int],
+        "amrb_exchange_get_timing": [vp, C.POINTER(C.c_double)],
         "amrb_exchange_push": [vp, C.c_int, sz],
         "amrb_exchange_wait": [vp, C.c_int, sz],
         "amrb_pool_apply_plan": [vp, sz, i8p, i32p, i8p],

@@ -180,6 +180,11 @@ struct amrb_exchange
     cudaEvent_t  ev_boundary = nullptr, ev_push = nullptr;
     int          slab_doubles = 0;          // per entry, all fields
     uint64_t     launches = 0;
+    // optional per-phase timing of the plain schedule (amrb_exchange_set_timing): events around push / wait /
+    // unpack / step of every step of a batch
+    bool                     timing = false;
+    std::vector<cudaEvent_t> tev;
+    size_t                   tsteps = 0;
 };
 
 namespace
@@ -317,6 +322,7 @@ amrb_status amrb_exchange_destroy(amrb_exchange* ex)
     if (ex->ev_boundary) cudaEventDestroy(ex->ev_boundary);
     if (ex->ev_push) cudaEventDestroy(ex->ev_push);
     if (ex->h_timeout) cudaFreeHost(ex->h_timeout);
+    for (cudaEvent_t e : ex->tev) cudaEventDestroy(e);
     cudaGetLastError();
     delete ex;
     return AMRB_OK;
@@ -399,7 +405,11 @@ amrb_status amrb_exchange_set_lists(amrb_exchange* ex, const int32_t* boundary, 
     }
     if (!ex->side)
     {
-        AMRB_CUDA(cudaStreamCreateWithFlags(&ex->side, cudaStreamNonBlocking));
+        // highest priority: the push CTAs must be dispatched ahead of the persistent CTAs of the interior launch
+        // (which take the whole register file of an SM once resident)
+        int lo = 0, hi = 0;
+        AMRB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        AMRB_CUDA(cudaStreamCreateWithPriority(&ex->side, cudaStreamNonBlocking, hi));
         AMRB_CUDA(cudaEventCreateWithFlags(&ex->ev_boundary, cudaEventDisableTiming));
         AMRB_CUDA(cudaEventCreateWithFlags(&ex->ev_push, cudaEventDisableTiming));
     }
@@ -424,11 +434,39 @@ amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, d
     auto slot = [&](size_t k) { return reinterpret_cast<unsigned long long*>(amrb_pool_dtmin_slot(p, k)); };
     if (!ov)
     {
+        if (ex->timing)
+        {
+            while (ex->tev.size() < 4 * steps + 1)
+            {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) return fail(AMRB_ERR_CUDA, "cudaEventCreate");
+                ex->tev.push_back(e);
+            }
+            ex->tsteps = steps;
+            cudaEventRecord(ex->tev[0], p->stream);
+        }
         for (size_t k = 0; k < steps && s == AMRB_OK; ++k)
         {
             s = push(ex, slot(k));
-            if (s == AMRB_OK) s = wait_and_unpack(ex, slot(k));
+            if (ex->timing) cudaEventRecord(ex->tev[4 * k + 1], p->stream);
+            if (s == AMRB_OK)
+            {
+                // wait and unpack timed separately
+                exchange_wait_kernel<<<1, 32, 0, p->stream>>>(ex->box, ex->world, ex->rank, ex->gen, ex->tgen, slot(k),
+                                                              ex->h_timeout, 8000000000ll);
+                ++ex->launches;
+                if (ex->timing) cudaEventRecord(ex->tev[4 * k + 2], p->stream);
+                if (ex->n_recv)
+                {
+                    p->ops->faces(p->stream, p->cur, ex->d_recv, (int)ex->n_recv, ex->recv[ex->gen & 1], 1);
+                    ++ex->launches;
+                }
+                if (ex->timing) cudaEventRecord(ex->tev[4 * k + 3], p->stream);
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) s = fail(AMRB_ERR_CUDA, std::string("exchange wait / unpack: ") + cudaGetErrorString(e));
+            }
             if (s == AMRB_OK) s = amrb_pool_step_partial(p, nullptr, 0);
+            if (ex->timing) cudaEventRecord(ex->tev[4 * k + 4], p->stream);
             if (s == AMRB_OK) s = amrb_pool_step_commit(p);
         }
     }
@@ -490,6 +528,30 @@ amrb_status amrb_exchange_wait(amrb_exchange* ex, int with_dt, size_t k)
     unsigned long long* slot = with_dt ? reinterpret_cast<unsigned long long*>(amrb_pool_dtmin_slot(ex->pool, k)) : nullptr;
     if (with_dt && !slot) return fail(AMRB_ERR_STATE, "no dt-min slot: open a batch first");
     return wait_and_unpack(ex, slot);
+}
+
+// per-phase device times [ms] of the last batch run with the plain schedule after amrb_exchange_set_timing(ex, 1):
+// out[0..3] = push, wait (skew + flags), unpack, fused step, summed over the batch's steps
+amrb_status amrb_exchange_set_timing(amrb_exchange* ex, int on)
+{
+    if (!ex) return fail(AMRB_ERR_ARGUMENT, "null exchange");
+    ex->timing = on != 0;
+    return AMRB_OK;
+}
+amrb_status amrb_exchange_get_timing(amrb_exchange* ex, double* out4)
+{
+    if (!ex || !out4) return fail(AMRB_ERR_ARGUMENT, "null argument");
+    for (int i = 0; i < 4; ++i) out4[i] = 0.0;
+    if (!ex->timing || ex->tsteps == 0) return fail(AMRB_ERR_STATE, "no timed batch");
+    AMRB_CUDA(cudaStreamSynchronize(ex->pool->stream));
+    for (size_t k = 0; k < ex->tsteps; ++k)
+        for (int i = 0; i < 4; ++i)
+        {
+            float ms = 0.f;
+            AMRB_CUDA(cudaEventElapsedTime(&ms, ex->tev[4 * k + i], ex->tev[4 * k + i + 1]));
+            out4[i] += ms;
+        }
+    return AMRB_OK;
 }
 
 // 1 when a wait kernel gave up on a peer since the last call (the state is then undefined)

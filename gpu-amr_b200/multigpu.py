@@ -821,6 +821,24 @@ def run_bench(args, METRIC, UNIT):
     ms_total = sorted(reps)[len(reps) // 2]
     value = cells * K / (ms_total * 1e-3)
 
+    # per-phase device times of one more K-step batch (peer-memory transport, plain schedule), max over ranks
+    phases = None
+    if sol.ex is not None:
+        import ctypes as C
+        B.check(sol.L.amrb_exchange_set_timing(sol.ex, 1))
+        dist.barrier()
+        sol.advance_batch_async(K, overlap=False)
+        sol.finish_advance_batch()
+        out4 = (C.c_double * 4)()
+        B.check(sol.L.amrb_exchange_get_timing(sol.ex, out4))
+        B.check(sol.L.amrb_exchange_set_timing(sol.ex, 0))
+        ph = torch.tensor(list(out4), dtype=torch.float64, device="cuda") / K
+        pmax, pmin = ph.clone(), ph.clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        phases = {n: {"max_over_ranks": float(pmax[i]), "min_over_ranks": float(pmin[i])}
+                  for i, n in enumerate(("push", "wait", "unpack", "step_kernel"))}
+
     # e2e: pinned-host state -> device, halo, K steps, state back to the host (per rank its shard)
     n_own, stored = sol.plan.n_owned, sol.pool.stored
     fbytes = n_own * stored * 8
@@ -880,6 +898,7 @@ def run_bench(args, METRIC, UNIT):
                                              ("interior patches overlap the slab exchange" if overlap else
                                               "exchange, then one launch over all patches")),
                        "schedule_probe_ms_per_6_steps": {"overlap": mode_ms[True], "single_launch": mode_ms[False]},
+                       "ms_per_step_by_phase": phases,
                        "ghost_patches_max_rank": int(mx[2].item()), "boundary_patches_max_rank": int(mx[3].item()),
                        "ghost_bytes_per_step_all_ranks": float(tot[1].item())})
         line = {

@@ -282,6 +282,9 @@ amrb_status amrb_exchange_set_lists(amrb_exchange* ex, const int32_t* boundary, 
  * CFL minimum of slot k of the open batch */
 amrb_status amrb_exchange_push(amrb_exchange* ex, int with_dt, size_t k);
 amrb_status amrb_exchange_wait(amrb_exchange* ex, int with_dt, size_t k);
+/* per-phase device times [ms] of the last batch (plain schedule): out4 = push, wait, unpack, fused step */
+amrb_status amrb_exchange_set_timing(amrb_exchange* ex, int on);
+amrb_status amrb_exchange_get_timing(amrb_exchange* ex, double* out4);
 /* 1 when a receiver gave up waiting for a peer since the last call (state undefined afterwards) */
 int         amrb_exchange_timed_out(amrb_exchange* ex);
 uint64_t    amrb_exchange_launch_count(const amrb_exchange* ex);

@@ -145,14 +145,8 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
         for (int i = 0; i < NT3; ++i)
         {
             const int w = lane + 32 * i, j = w / 10, c = w % 10;
-            if (j >= np) continue;
-            const int p = patch_of(item0 + j);
-            if (c < 8)
-                t.r[i] = __ldg(a.nbr + (size_t)p * 8 + c);
-            else if (c == 8)
-                t.r[i] = (int)__ldg(reinterpret_cast<const uint32_t*>(a.meta) + p);
-            else
-                t.r[i] = __ldg(a.level + p);
+            const int p = patch_of(item0 + ((j < np) ? j : 0));
+            t.r[i]      = tab_piece2(a.nbr, a.level, a.meta, p, c, j < np);
         }
         return t;
     };

@@ -81,10 +81,7 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
         if (k >= nt) return 0;
         int p, z0;
         task_of(k, p, z0);
-        if (lane < 24) return __ldg(a.nbr + (size_t)p * 24 + lane);
-        if (lane == 24) return __ldg(a.level + p);
-        if (lane < 31) return (int)__ldg(a.meta + (size_t)p * 6 + (lane - 25));
-        return 0;
+        return tab_piece3(a.nbr, a.level, a.meta, p, lane);
     };
     // request task k: the bulk copy of its planes and the gather of its lateral ghost cells (tab = its tables)
     auto request = [&](int k, int tab) {
@@ -103,7 +100,7 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
         {
             const int sd = e / (S * ZT), r = e % (S * ZT), zl = r / S, t = r % S;
             const int d  = (sd < 2) ? 4 + sd : sd;      // tree direction: x-, x+, y-, y+
-            const int m  = __shfl_sync(0xffffffffu, tab, 25 + d);
+            const int m  = tab_meta3(tab, p, d);
             const int rel = m & 3;
             const int z   = z0 + zl;
             // neighbor index this ghost cell reads: the first one, or for a finer neighbor the one covering it

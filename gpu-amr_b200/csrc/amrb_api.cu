@@ -784,7 +784,7 @@ amrb_status amrb_pool_set_topology(amrb_pool* p, size_t n_owned, size_t n_total,
         p->table_cap = 0;
         const size_t cap = std::max(n_owned, std::min(p->capacity, n_owned * 2));
         AMRB_CUDA(cudaMalloc(&p->d_nbr, cap * ND * KF * sizeof(int32_t)));
-        AMRB_CUDA(cudaMalloc(&p->d_meta, cap * ND));
+        AMRB_CUDA(cudaMalloc(&p->d_meta, cap * ND + 4)); // + 4: the kernels read the bytes as aligned words
         AMRB_CUDA(cudaMalloc(&p->d_level, cap * sizeof(int32_t)));
         p->table_cap = cap;
     }
@@ -826,7 +826,7 @@ amrb_status amrb_pool_set_topology_from_ids(amrb_pool* p, const uint64_t* ids, s
         p->table_cap = 0;
         const size_t cap = std::max(n, std::min(p->capacity, n * 2));
         AMRB_CUDA(cudaMalloc(&p->d_nbr, cap * ND * KF * sizeof(int32_t)));
-        AMRB_CUDA(cudaMalloc(&p->d_meta, cap * ND));
+        AMRB_CUDA(cudaMalloc(&p->d_meta, cap * ND + 4)); // + 4: the kernels read the bytes as aligned words
         AMRB_CUDA(cudaMalloc(&p->d_level, cap * sizeof(int32_t)));
         p->table_cap = cap;
     }
@@ -1486,7 +1486,7 @@ amrb_status raw_tables(size_t records, int rank, cudaStream_t st, bool zero)
         g_raw.cap = 0;
         const size_t cap = records * 2;
         AMRB_CUDA(cudaMalloc(&g_raw.nbr, cap * 4 * sizeof(int32_t)));
-        AMRB_CUDA(cudaMalloc(&g_raw.meta, cap));
+        AMRB_CUDA(cudaMalloc(&g_raw.meta, cap + 4));
         g_raw.cap = cap;
     }
     if (!g_raw.scal)

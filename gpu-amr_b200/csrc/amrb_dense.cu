@@ -44,15 +44,15 @@ struct DenseInst
         const int grid  = std::max(1, std::min(device_sm_count() * MINB, (tasks + WPC - 1) / WPC));
         k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
     }
-    template <int CR, int NS, int WPC, int MAXREG, int CTAS>
-    static void march_r(cudaStream_t st, const StepArgs& a, int n_items)
+    template <int CR, int NS, int WPC, int MINB, int OPT>
+    static void march_o(cudaStream_t st, const StepArgs& a, int n_items)
     {
         using MC = March3DenseCfg<S, CR, NS, WPC>;
-        auto k   = euler3d_dense_kernel_r<S, CR, NS, WPC, MAXREG>;
+        auto k   = euler3d_dense_kernel_o<S, CR, NS, WPC, MINB, OPT>;
         static DevicePrepared prepared;
         if (!prepared.ensure((const void*)k, (int)MC::SMEM)) return;
         const int tasks = n_items * MC::NB;
-        const int grid  = std::max(1, std::min(device_sm_count() * CTAS, (tasks + WPC - 1) / WPC));
+        const int grid  = std::max(1, std::min(device_sm_count() * MINB, (tasks + WPC - 1) / WPC));
         k<<<grid, WPC * 32, MC::SMEM, st>>>(a, n_items);
     }
     template <int WPC, int MINB>
@@ -72,22 +72,19 @@ struct DenseInst
         {
             // variant (amrb_pool_set_variant): ring shape A/B.  0 = chunks of 4 planes (2 KB bulk copies),
             // 2 stages (8^3) / 1-plane cp.async chunks, 4 stages (16^3); 21 = 2-plane chunks, 3 stages;
-            // 22 = 2-plane chunks, 2 stages, 3 CTAs per SM (12 warps); 25 / 26 / 27 = 10 / 9 / 12 warps per SM
-            // with explicit register budgets (__maxnreg__)
+            // 28 = two planes per loop trip; 41 / 44 = body options (amrb_march_euler3d_dense.cuh: kOpt*); all within
+            // 1 % of variant 0 (profiles/r02_summary.md).  Earlier A/B runs, removed again: 3 CTAs per SM with 2-plane
+            // chunks, 9 / 10 / 12 warps per SM under __maxnreg__ (slower: spills), one CTA per SM (5.29 vs 3.53 ms)
             if constexpr (S == 8)
             {
                 if (a.variant == 21)
                     march<2, 3, 4, 2>(st, a, n_items);
-                else if (a.variant == 22)
-                    march<2, 2, 4, 3>(st, a, n_items);
                 else if (a.variant == 28)
                     march_pp<4, 2, 4, 2>(st, a, n_items); // two planes per loop trip, no state copies
-                else if (a.variant == 25)
-                    march_r<2, 3, 5, 200, 2>(st, a, n_items); // 10 warps per SM, 200 registers
-                else if (a.variant == 26)
-                    march_r<4, 2, 3, 224, 3>(st, a, n_items); // 9 warps per SM, 224 registers
-                else if (a.variant == 27)
-                    march_r<2, 2, 6, 168, 2>(st, a, n_items); // 12 warps per SM as 2 CTAs of 6 warps
+                else if (a.variant == 41)
+                    march_o<4, 2, 4, 2, kOptPrefetch>(st, a, n_items); // task prologue gathered one task ahead
+                else if (a.variant == 44)
+                    march_o<4, 2, 4, 2, kOptPrefetch | kOptOneBlock | kOptEarlyZ>(st, a, n_items);
                 else
                     march<4, 2, 4, 2>(st, a, n_items);
             }

@@ -63,6 +63,54 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
 }
 
 // ---- TMA 1-D bulk copy (cp.async.bulk) + mbarrier: SASS UBLKCP / SYNCS ------------------------
+// Predicated read-only loads for the per-lane pieces of a patch's halo tables (neighbor indices, level,
+// relation bytes: three arrays, one piece per lane).  Written as `if (lane < 24) return ldg(..); if (lane == 24)
+// return ldg(..); ...` the divergent paths run one after the other AND share their destination register, so
+// each path waits for the previous path's load to land: a full memory latency per path (10 % of the warp time
+// of advect3d_dense_kernel, profiles/r02i_advect3d_dense_ncu_summary.txt).  These issue back to back.
+__device__ __forceinline__ int ldg_s32_if(const void* p, bool take, int otherwise)
+{
+    int v = otherwise;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.s32 %0, [%1];\n\t}"
+        : "+r"(v)
+        : "l"(p), "r"((int)take));
+    return v;
+}
+__device__ __forceinline__ int ldg_u8_if(const void* p, bool take, int otherwise)
+{
+    int v = otherwise;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.u8 %0, [%1];\n\t}"
+        : "+r"(v)
+        : "l"(p), "r"((int)take));
+    return v;
+}
+// 3D tables of patch q: lanes 0-23 the 6 x 4 neighbor indices, lane 24 the level, lanes 25-30 the aligned 32-bit
+// word that holds the relation byte of direction lane-25 (ONE load instruction for all lanes; tab_meta3 picks the
+// byte at the point of use -- the byte arrays are allocated with 4 spare bytes), lane 31 q itself
+__device__ __forceinline__ int tab_piece3(const int32_t* nbr, const int32_t* level, const uint8_t* meta, int q,
+                                          int lane)
+{
+    const size_t   mb  = ((size_t)q * 6 + (size_t)(lane >= 25 ? lane - 25 : 0)) & ~(size_t)3;
+    const int32_t* p32 = (lane < 24)    ? nbr + (size_t)q * 24 + lane
+                         : (lane == 24) ? level + q
+                                        : reinterpret_cast<const int32_t*>(meta + mb);
+    return ldg_s32_if(p32, lane < 31, q);
+}
+// relation byte (rel | quadrant << 2) of direction d of patch q out of the warp's table pieces
+__device__ __forceinline__ int tab_meta3(int tab, int q, int d)
+{
+    const int w = __shfl_sync(0xffffffffu, tab, 25 + d);
+    return (w >> ((((q & 1) * 2 + d) & 3) * 8)) & 0xff;
+}
+// 2D tables of patch q, piece c: 0-7 the 4 x 2 neighbor indices, 8 the 4 relation bytes, 9 the level
+__device__ __forceinline__ int tab_piece2(const int32_t* nbr, const int32_t* level, const uint8_t* meta, int q,
+                                          int c, bool take)
+{
+    const int32_t* p32 = (c < 8) ? nbr + (size_t)q * 8 + c
+                                 : (c == 8 ? reinterpret_cast<const int32_t*>(meta) + q : level + q);
+    return ldg_s32_if(p32, take && c < 10, 0);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -208,10 +208,7 @@ euler2d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     auto tab_load = [&](int k) -> int {
         int q, r;
         task_of(k, q, r);
-        if (lane < 8) return __ldg(a.nbr + (size_t)q * 8 + lane);
-        if (lane == 8) return (int)__ldg(reinterpret_cast<const uint32_t*>(a.meta) + q);
-        if (lane == 9) return __ldg(a.level + q);
-        return 0;
+        return tab_piece2(a.nbr, a.level, a.meta, q, lane, true);
     };
     int tab = (nt > 0) ? tab_load(0) : 0;
 

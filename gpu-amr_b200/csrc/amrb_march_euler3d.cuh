@@ -246,10 +246,8 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
     auto tab_load = [&](int tau) -> int {
         const int item = tau / C::NB;
         const int q    = a.list ? a.list[item] : item;
-        if (lane < 24) return __ldg(a.nbr + (size_t)q * (G::NDIR * G::KF) + lane);
-        if (lane == 24) return __ldg(a.level + q);
-        if (lane < 31) return (int)__ldg(a.meta + (size_t)q * G::NDIR + (lane - 25));
-        return 0;
+        static_assert(G::NDIR * G::KF == 24, "3D tables");
+        return tab_piece3(a.nbr, a.level, a.meta, q, lane);
     };
     int tab = (tau_cur < n_tasks) ? tab_load(tau_cur) : 0, tab_nxt = 0;
 
@@ -394,7 +392,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         GhostSrc3 gs;
         {
             // relation byte and the four neighbor indices of the side, from the prefetched tables
-            const int bm = __shfl_sync(0xffffffffu, tab, 25 + bd);
+            const int bm = tab_meta3(tab, p, bd);
             int4      bnb;
             bnb.x = __shfl_sync(0xffffffffu, tab, bd * 4);
             bnb.y = __shfl_sync(0xffffffffu, tab, bd * 4 + 1);
@@ -499,7 +497,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
         };
         // ghost cells of this lane's column pair across the z faces (d = 0 below, 1 above)
         auto zghost = [&](int d, double (&vA)[NV], double (&vB)[NV]) {
-            const int m = __shfl_sync(0xffffffffu, tab, 25 + d);
+            const int m = tab_meta3(tab, p, d);
             int4      nb;
             nb.x = __shfl_sync(0xffffffffu, tab, d * 4);
             nb.y = __shfl_sync(0xffffffffu, tab, d * 4 + 1);

@@ -39,7 +39,8 @@ struct March3DenseCfg
     static constexpr int BFW   = 6;                    // doubles per parked boundary flux (5 + pad)
     static constexpr int BF    = 2 * 32 * BFW;         // double-buffered, 32 lateral faces per plane
     static constexpr int ST    = 5 * 32;               // ghost cells of the next plane's faces in flight
-    static constexpr int WARP_DOUBLES = RING + BF + ST;
+    static constexpr int GZ    = 5 * 64;               // ghost plane below the NEXT task's first plane, in flight
+    static constexpr int WARP_DOUBLES = RING + BF + ST + GZ;
     static constexpr size_t SMEM      = (size_t)WPC * WARP_DOUBLES * sizeof(double);
     static_assert(S % 8 == 0, "8 x 8 column blocks");
     static_assert(S % CR == 0, "chunk shape");
@@ -47,9 +48,20 @@ struct March3DenseCfg
     static_assert((FS * 8) % 16 == 0 && (WARP_DOUBLES * 8) % 16 == 0, "bulk copy alignment");
 };
 
-template <int S, int CR, int NS, int WPC, bool PINGPONG = false>
+// OPT bits: 1 = two planes per loop trip (ping-pong plane states); 2 = task prologue pipelined into the previous
+// task (ghost cells of plane 0's faces and the ghost plane below gathered with cp.async during the previous task's
+// last plane flux + stores: no global-memory latency at a task switch); 4 = one basic block per plane (the
+// next-step wave speeds of plane 0's dummy pass are computed and discarded instead of branched around);
+// 8 = the lower z-face flux enters the accumulators first (10 fewer doubles live across the x / y faces)
+constexpr int kOptPingPong = 1, kOptPrefetch = 2, kOptOneBlock = 4, kOptEarlyZ = 8;
+
+template <int S, int CR, int NS, int WPC, int OPT = 0>
 __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_items)
 {
+    constexpr bool PINGPONG = (OPT & kOptPingPong) != 0;
+    constexpr bool PF       = (OPT & kOptPrefetch) != 0;
+    constexpr bool ONEBLOCK = (OPT & kOptOneBlock) != 0;
+    constexpr bool EARLYZ   = (OPT & kOptEarlyZ) != 0;
     using C           = March3DenseCfg<S, CR, NS, WPC>;
     constexpr int NV  = 5;
     constexpr int SS  = C::SS;
@@ -68,6 +80,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
     double*   ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::WARP_DOUBLES;
     double*   sBF  = ring + C::RING;
     double*   sST  = sBF + C::BF + lane; // this lane's column of the ghost staging buffer
+    double*   sGZ  = sBF + C::BF + C::ST + 2 * lane; // this lane's (A | B) slots of the staged ghost plane
     uint64_t* bar  = bars + warp * NS;
 
     // ---- this warp's tasks: first one static (warp gw takes task gw: the chip starts on one Morton
@@ -76,47 +89,41 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
     const int gw = blockIdx.x * WPC + warp, nw_all = gridDim.x * WPC;
     int          tau_cur = (gw < n_tasks) ? gw : n_tasks; // n_tasks = "none"
     int          tau_nxt = n_tasks;
-    unsigned int nxt_raw = 0;
-    bool         nxt_known = true;
-    int          kc = 0; // sequence number of the current task
-    auto fetch_next = [&]() {
+    unsigned int nxt_raw = 0; // lane 0: the ticket drawn for the task after the current one
+    int          kc = 0;      // sequence number of the current task
+    // Tickets run one task ahead of their use: the one read at plane 2 of task k (-> task k+1) was drawn at plane 2
+    // of task k-1, and the next one is drawn right after the read.  (Drawn at the end of a task and read "later",
+    // the compiler moved the read up to the atomic: its whole latency, 1.6 % of the warp time, per task.)
+    auto draw_ticket = [&]() {
+        if (a.queue != nullptr && lane == 0) nxt_raw = atomicAdd(a.queue, 1u);
+    };
+    auto take_next = [&]() {
         if (a.queue == nullptr)
-        {
-            tau_nxt   = tau_cur + nw_all;
-            nxt_known = true;
-        }
+            tau_nxt = tau_cur + nw_all;
         else
         {
-            if (lane == 0) nxt_raw = atomicAdd(a.queue, 1u);
-            nxt_known = false;
+            const unsigned int t = __shfl_sync(0xffffffffu, nxt_raw, 0);
+            tau_nxt              = (t < 0x40000000u) ? nw_all + (int)t : n_tasks;
+            draw_ticket();
         }
     };
-    auto resolve_next = [&]() {
-        if (nxt_known) return;
-        const unsigned int t = __shfl_sync(0xffffffffu, nxt_raw, 0);
-        tau_nxt              = (t < 0x40000000u) ? nw_all + (int)t : n_tasks;
-        nxt_known            = true;
-    };
-    if (tau_cur < n_tasks) fetch_next();
+    static_assert(S - NS * CR + CR - 1 >= 2, "the ring reaches the next task only after plane 2 (take_next)");
+    if (tau_cur < n_tasks) draw_ticket();
 
     // halo tables of a task's patch, one 32-bit piece per lane (lanes 0-23: 6 x 4 neighbor indices,
     // lane 24: level, lanes 25-30: the 6 relation bytes), prefetched for the NEXT task
     auto tab_load = [&](int tau) -> int {
         const int item = tau / C::NB;
         const int q    = a.list ? a.list[item] : item;
-        if (lane < 24) return __ldg(a.nbr + (size_t)q * 24 + lane);
-        if (lane == 24) return __ldg(a.level + q);
-        if (lane < 31) return (int)__ldg(a.meta + (size_t)q * 6 + (lane - 25));
-        return 0;
+        return tab_piece3(a.nbr, a.level, a.meta, q, lane); // lane 31: q (a.list resolved with the prefetch)
     };
     int tab = (tau_cur < n_tasks) ? tab_load(tau_cur) : 0, tab_nxt = 0;
 
-    auto task_at = [&](int tau, int& p, int& bx, int& by) {
-        const int item = tau / C::NB;
-        const int blk  = tau % C::NB;
-        bx             = blk % C::NBX;
-        by             = blk / C::NBX;
-        p              = a.list ? a.list[item] : item;
+    auto task_at = [&](int tau, int tabv, int& p, int& bx, int& by) {
+        const int blk = tau % C::NB;
+        bx            = blk % C::NBX;
+        by            = blk / C::NBX;
+        p             = __shfl_sync(0xffffffffu, tabv, 31);
     };
 
     if (lane == 0)
@@ -129,11 +136,10 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
     // ---- producer side of the ring (lane 0 issues the bulk copies; all lanes track the counters)
     int  ik = 0, ic = 0, ist = 0; // next chunk to issue: task, chunk in task, stage
     auto issue_next = [&]() {
-        if (ik != kc) resolve_next();
         const int tau = (ik == kc) ? tau_cur : tau_nxt;
         if (tau >= n_tasks) return;
         int p, bx, by;
-        task_at(tau, p, bx, by);
+        task_at(tau, (ik == kc) ? tab : tab_nxt, p, bx, by);
         double* dst = ring + ist * C::STAGE;
         if constexpr (C::WHOLE)
         {
@@ -188,28 +194,11 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
 
     int cst = 0, cph = 0; // consumer: stage and phase parity of the next chunk to wait for
 
-    while (tau_cur < n_tasks)
-    {
-        int p, bx, by;
-        task_at(tau_cur, p, bx, by);
-        const int lvl = __shfl_sync(0xffffffffu, tab, 24);
-        if (lvl != lvl_prev && lvl_prev >= 0)
-        {
-            if (sxm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][0] / sxm);
-            if (sym > 1e-12) cand = fmin(cand, a.dx[lvl_prev][1] / sym);
-            if (szm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][2] / szm);
-            sxm = sym = szm = 0.0;
-        }
-        lvl_prev         = lvl;
-        const double hx  = -0.5 * (dt / a.dx[lvl][0]); // -0.5 dt/dx, x = fastest layout dim
-        const double hy  = -0.5 * (dt / a.dx[lvl][1]);
-        const double hz  = -0.5 * (dt / a.dx[lvl][2]);
-        const double nhz = -hz;
-        const size_t pb  = (size_t)p * N;
-        const int    x0 = 8 * bx, y0 = 8 * by; // interior coordinates of the block's first cell
-
-        // ---- boundary-face role of this lane for the task: where the ghost cell of plane z comes
-        // from, resolved ONCE per task (interior coordinates; gy / gx may be -1 or S = across a face)
+    // ---- boundary-face role of this lane for a task: where the ghost cell of plane z comes from, resolved
+    // ONCE per task (interior coordinates; gy / gx may be -1 or S = across a face)
+    GhostSrc3 gs;
+    auto resolve_gs = [&](int tabv, int p, int bx, int by) {
+        const int  x0 = 8 * bx, y0 = 8 * by;
         const int  bd       = (side < 2) ? 4 + side : side; // tree direction of the side
         const bool internal = (side == 0)   ? (bx > 0)
                               : (side == 1) ? (bx < C::NBX - 1)
@@ -228,76 +217,194 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             g_y       = (side == 3) ? y0 + 8 : y0 - 1;
             i_y       = (side == 3) ? y0 + 7 : y0;
         }
-        const int ioff_s = (i_y - y0) * S + i_x; // interior cell inside the staged block rows
-        GhostSrc3 gs;
+        const int bm = tab_meta3(tabv, p, bd);
+        int4      bnb;
+        bnb.x = __shfl_sync(0xffffffffu, tabv, bd * 4);
+        bnb.y = __shfl_sync(0xffffffffu, tabv, bd * 4 + 1);
+        bnb.z = __shfl_sync(0xffffffffu, tabv, bd * 4 + 2);
+        bnb.w = __shfl_sync(0xffffffffu, tabv, bd * 4 + 3);
+        const int rel = internal ? 0 : (bm & 3);
+        int f_y = g_y, f_x = g_x; // mirrored into the neighbor's frame (patch_utils.hpp:322-327)
+        if (!internal)
         {
-            const int bm = __shfl_sync(0xffffffffu, tab, 25 + bd);
-            int4      bnb;
-            bnb.x = __shfl_sync(0xffffffffu, tab, bd * 4);
-            bnb.y = __shfl_sync(0xffffffffu, tab, bd * 4 + 1);
-            bnb.z = __shfl_sync(0xffffffffu, tab, bd * 4 + 2);
-            bnb.w = __shfl_sync(0xffffffffu, tab, bd * 4 + 3);
-            const int rel = internal ? 0 : (bm & 3);
-            int f_y = g_y, f_x = g_x; // mirrored into the neighbor's frame (patch_utils.hpp:322-327)
-            if (!internal)
-            {
-                if (side < 2)
-                    f_x += (side & 1) ? -S : S;
-                else
-                    f_y += (side & 1) ? -S : S;
-            }
-            gs.finer  = 0;
-            gs.zshift = 0;
-            gs.zbase  = 0;
-            gs.q0 = gs.q1 = p;
-            if (internal)
-                gs.off = g_y * S + g_x; // block side inside the patch: the own patch's cell
-            else if (rel == 1)
-            {
-                gs.q0 = gs.q1 = bnb.x; // same_t (patch_utils.hpp:315-332)
-                gs.off        = f_y * S + f_x;
-            }
-            else if (rel == 3)
-            {
-                // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
-                const int qz = (bm >> 2) & 1, qy = (bm >> 3) & 1, qx = (bm >> 4) & 1;
-                gs.q0 = gs.q1 = bnb.x;
-                gs.off    = (qy * HF + f_y / 2) * S + (qx * HF + f_x / 2);
-                gs.zbase  = qz * HF;
-                gs.zshift = 1;
-            }
-            else if (rel == 2)
-            {
-                // finer_t: mean of 8 fine cells (patch_utils.hpp:334-386); finer-neighbor index =
-                // z half (bit 0) + 2 x half along the other tangential dim (neighbor.hpp:316-337)
-                const int t = ((side < 2) ? g_y : g_x) / HF;
-                gs.q0       = t ? bnb.z : bnb.x;
-                gs.q1       = t ? bnb.w : bnb.y;
-                gs.off      = ((f_y * 2) % S) * S + ((f_x * 2) % S);
-                gs.finer    = 1;
-            }
+            if (side < 2)
+                f_x += (side & 1) ? -S : S;
             else
-                gs.off = i_y * S + i_x; // relation "none" (never in a periodic balanced tree): zero gradient
+                f_y += (side & 1) ? -S : S;
         }
-        // ghost cell of this lane's boundary face of plane z -> staging column (asynchronously)
-        auto bnd_issue = [&](int z) {
-            double* st = sST;
-            if (gs.finer)
-            {
-                const size_t o =
-                    (size_t)(z < HF ? gs.q0 : gs.q1) * N + (size_t)(2 * (z % HF)) * SS + gs.off;
-                double t[NV];
-                fine_mean5(a.cur, o, S, SS, t);
+        gs.finer  = 0;
+        gs.zshift = 0;
+        gs.zbase  = 0;
+        gs.q0 = gs.q1 = p;
+        if (internal)
+            gs.off = g_y * S + g_x; // block side inside the patch: the own patch's cell
+        else if (rel == 1)
+        {
+            gs.q0 = gs.q1 = bnb.x; // same_t (patch_utils.hpp:315-332)
+            gs.off        = f_y * S + f_x;
+        }
+        else if (rel == 3)
+        {
+            // coarser_t: injection of the covering coarse cell (patch_utils.hpp:388-441)
+            const int qz = (bm >> 2) & 1, qy = (bm >> 3) & 1, qx = (bm >> 4) & 1;
+            gs.q0 = gs.q1 = bnb.x;
+            gs.off    = (qy * HF + f_y / 2) * S + (qx * HF + f_x / 2);
+            gs.zbase  = qz * HF;
+            gs.zshift = 1;
+        }
+        else if (rel == 2)
+        {
+            // finer_t: mean of 8 fine cells (patch_utils.hpp:334-386); finer-neighbor index =
+            // z half (bit 0) + 2 x half along the other tangential dim (neighbor.hpp:316-337)
+            const int t = ((side < 2) ? g_y : g_x) / HF;
+            gs.q0       = t ? bnb.z : bnb.x;
+            gs.q1       = t ? bnb.w : bnb.y;
+            gs.off      = ((f_y * 2) % S) * S + ((f_x * 2) % S);
+            gs.finer    = 1;
+        }
+        else
+            gs.off = i_y * S + i_x; // relation "none" (never in a periodic balanced tree): zero gradient
+    };
+    // ghost cell of this lane's boundary face of plane z -> staging column (asynchronously)
+    auto bnd_issue = [&](int z) {
+        double* st = sST;
+        if (gs.finer)
+        {
+            const size_t o = (size_t)(z < HF ? gs.q0 : gs.q1) * N + (size_t)(2 * (z % HF)) * SS + gs.off;
+            double       t[NV];
+            fine_mean5(a.cur, o, S, SS, t);
 #pragma unroll
-                for (int f = 0; f < NV; ++f) st[f * 32] = t[f];
-            }
-            else
-            {
-                const size_t o = (size_t)gs.q0 * N + (size_t)(gs.zbase + (z >> gs.zshift)) * SS + gs.off;
+            for (int f = 0; f < NV; ++f) st[f * 32] = t[f];
+        }
+        else
+        {
+            const size_t o = (size_t)gs.q0 * N + (size_t)(gs.zbase + (z >> gs.zshift)) * SS + gs.off;
 #pragma unroll
-                for (int f = 0; f < NV; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
+            for (int f = 0; f < NV; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
+        }
+    };
+    // source of the ghost cells of this lane's column pair across a z face (d = 0 below, 1 above)
+    struct ZSrc
+    {
+        size_t o;
+        int    dB, fin;
+    };
+    auto zsource = [&](int d, int tabv, int p, int bx, int by) -> ZSrc {
+        const int m = tab_meta3(tabv, p, d);
+        int4      nb;
+        nb.x = __shfl_sync(0xffffffffu, tabv, d * 4);
+        nb.y = __shfl_sync(0xffffffffu, tabv, d * 4 + 1);
+        nb.z = __shfl_sync(0xffffffffu, tabv, d * 4 + 2);
+        nb.w = __shfl_sync(0xffffffffu, tabv, d * 4 + 3);
+        const int rel = m & 3;
+        const int y = 8 * by + yy, x = 8 * bx + 2 * xq; // interior coordinates of cell A
+        const int zf = d ? 0 : S - 1;                   // mirrored source plane of a same-level neighbor
+        int       q = p, dB = 1, fin = 0;
+        int       off = (d ? S - 1 : 0) * SS + y * S + x; // "none": the own boundary cell
+        if (rel == 1)
+        {
+            q   = nb.x;
+            off = zf * SS + y * S + x;
+        }
+        else if (rel == 3)
+        {
+            const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
+            q   = nb.x;
+            off = (qz * HF + zf / 2) * SS + (qy * HF + y / 2) * S + (qx * HF + x / 2);
+            dB  = 0;
+        }
+        else if (rel == 2)
+        {
+            const int fi = y / HF + 2 * (x / HF);
+            q            = (fi == 0) ? nb.x : (fi == 1) ? nb.y : (fi == 2) ? nb.z : nb.w;
+            off          = ((zf * 2) % S) * SS + ((y * 2) % S) * S + ((x * 2) % S);
+            dB           = 2;
+            fin          = 1;
+        }
+        return ZSrc{ (size_t)q * N + off, dB, fin };
+    };
+    // ... into registers
+    auto zghost = [&](int d, int tabv, int p, int bx, int by, double (&vA)[NV], double (&vB)[NV]) {
+        const ZSrc zs = zsource(d, tabv, p, bx, by);
+        if (zs.fin)
+        {
+            double tA[NV], tB[NV];
+            fine_mean5(a.cur, zs.o, S, SS, tA);
+            fine_mean5(a.cur, zs.o + 2, S, SS, tB);
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                vA[f] = tA[f];
+                vB[f] = tB[f];
             }
-        };
+        }
+        else
+        {
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                vA[f] = __ldg(a.cur.p[f] + zs.o);
+                vB[f] = __ldg(a.cur.p[f] + zs.o + zs.dB);
+            }
+        }
+    };
+    // ... into the staged ghost plane (asynchronously; the lane reads back only its own slots)
+    auto zghost_stage = [&](int tabv, int p, int bx, int by) {
+        const ZSrc zs = zsource(0, tabv, p, bx, by);
+        if (zs.fin)
+        {
+            double tA[NV], tB[NV];
+            fine_mean5(a.cur, zs.o, S, SS, tA);
+            fine_mean5(a.cur, zs.o + 2, S, SS, tB);
+#pragma unroll
+            for (int f = 0; f < NV; ++f) *reinterpret_cast<double2*>(sGZ + f * 64) = make_double2(tA[f], tB[f]);
+        }
+        else
+        {
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                cp_async8(sGZ + f * 64, a.cur.p[f] + zs.o);
+                cp_async8(sGZ + f * 64 + 1, a.cur.p[f] + zs.o + zs.dB);
+            }
+        }
+    };
+    // everything of a task that comes from global memory besides the ring: issued one task ahead
+    auto prefetch_task = [&](int tau, int tabv) {
+        int p, bx, by;
+        task_at(tau, tabv, p, bx, by);
+        resolve_gs(tabv, p, bx, by);
+        bnd_issue(0);
+        zghost_stage(tabv, p, bx, by);
+        cp_async_commit();
+    };
+    if constexpr (PF)
+    {
+        if (tau_cur < n_tasks) prefetch_task(tau_cur, tab);
+    }
+
+    while (tau_cur < n_tasks)
+    {
+        int p, bx, by;
+        task_at(tau_cur, tab, p, bx, by);
+        const int lvl = __shfl_sync(0xffffffffu, tab, 24);
+        if (lvl != lvl_prev && lvl_prev >= 0)
+        {
+            if (sxm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][0] / sxm);
+            if (sym > 1e-12) cand = fmin(cand, a.dx[lvl_prev][1] / sym);
+            if (szm > 1e-12) cand = fmin(cand, a.dx[lvl_prev][2] / szm);
+            sxm = sym = szm = 0.0;
+        }
+        lvl_prev         = lvl;
+        const double hx  = -0.5 * (dt / a.dx[lvl][0]); // -0.5 dt/dx, x = fastest layout dim
+        const double hy  = -0.5 * (dt / a.dx[lvl][1]);
+        const double hz  = -0.5 * (dt / a.dx[lvl][2]);
+        const double nhz = -hz;
+        const size_t pb  = (size_t)p * N;
+        const int    x0 = 8 * bx, y0 = 8 * by; // interior coordinates of the block's first cell
+        if constexpr (!PF) resolve_gs(tab, p, bx, by);
+        // interior cell of this lane's boundary face inside the staged block rows
+        const int ioff_s = (side < 2) ? bt * S + (side ? x0 + 7 : x0) : ((side == 3) ? 7 : 0) * S + x0 + bt;
         // flux of this lane's boundary face of plane z: ghost cell from the staging column, interior
         // cell from the staged plane (`pl` = first field of that plane inside the ring) -> sBF[z & 1].
         // G = F(ghost) + F(interior) -/+ smax (U_interior - U_ghost), one branch-free form for all sides.
@@ -334,71 +441,30 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             o[32]      = make_double2(F[2], F[3]);
             o[64]      = make_double2(F[4], 0.0);
         };
-        // ghost cells of this lane's column pair across the z faces (d = 0 below, 1 above)
-        auto zghost = [&](int d, double (&vA)[NV], double (&vB)[NV]) {
-            const int m = __shfl_sync(0xffffffffu, tab, 25 + d);
-            int4      nb;
-            nb.x = __shfl_sync(0xffffffffu, tab, d * 4);
-            nb.y = __shfl_sync(0xffffffffu, tab, d * 4 + 1);
-            nb.z = __shfl_sync(0xffffffffu, tab, d * 4 + 2);
-            nb.w = __shfl_sync(0xffffffffu, tab, d * 4 + 3);
-            const int rel = m & 3;
-            const int y = y0 + yy, x = x0 + 2 * xq;  // interior coordinates of cell A
-            const int zf = d ? 0 : S - 1;            // mirrored source plane of a same-level neighbor
-            int       q = p, dB = 1, fin = 0;
-            int       off = (d ? S - 1 : 0) * SS + y * S + x; // "none": the own boundary cell
-            if (rel == 1)
-            {
-                q   = nb.x;
-                off = zf * SS + y * S + x;
-            }
-            else if (rel == 3)
-            {
-                const int qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
-                q   = nb.x;
-                off = (qz * HF + zf / 2) * SS + (qy * HF + y / 2) * S + (qx * HF + x / 2);
-                dB  = 0;
-            }
-            else if (rel == 2)
-            {
-                const int fi = y / HF + 2 * (x / HF);
-                q            = (fi == 0) ? nb.x : (fi == 1) ? nb.y : (fi == 2) ? nb.z : nb.w;
-                off          = ((zf * 2) % S) * SS + ((y * 2) % S) * S + ((x * 2) % S);
-                dB           = 2;
-                fin          = 1;
-            }
-            const size_t o = (size_t)q * N + off;
-            if (fin)
-            {
-                double tA[NV], tB[NV];
-                fine_mean5(a.cur, o, S, SS, tA);
-                fine_mean5(a.cur, o + 2, S, SS, tB);
-#pragma unroll
-                for (int f = 0; f < NV; ++f)
-                {
-                    vA[f] = tA[f];
-                    vB[f] = tB[f];
-                }
-            }
-            else
-            {
-#pragma unroll
-                for (int f = 0; f < NV; ++f)
-                {
-                    vA[f] = __ldg(a.cur.p[f] + o);
-                    vB[f] = __ldg(a.cur.p[f] + o + dB);
-                }
-            }
-        };
-
         // ---- task prologue: ghost plane below, boundary fluxes of plane 0 (needs the task's first
         // chunk: it was requested while the previous task was marched)
         double gzA[NV], gzB[NV];
-        bnd_issue(0);
-        cp_async_commit();
-        zghost(0, gzA, gzB);
-        mbar_wait(&bar[cst], cph);
-        cp_async_wait<0>();
+        if constexpr (PF)
+        {
+            // both were gathered into shared memory while the previous task finished
+            mbar_wait(&bar[cst], cph);
+            cp_async_wait<0>();
+#pragma unroll
+            for (int f = 0; f < NV; ++f)
+            {
+                const double2 v = *reinterpret_cast<const double2*>(sGZ + f * 64);
+                gzA[f]          = v.x;
+                gzB[f]          = v.y;
+            }
+        }
+        else
+        {
+            bnd_issue(0);
+            cp_async_commit();
+            zghost(0, tab, p, bx, by, gzA, gzB);
+            mbar_wait(&bar[cst], cph);
+            cp_async_wait<0>();
+        }
         bnd_flux(0, ring + cst * C::STAGE);
         __syncwarp();
 
@@ -421,8 +487,13 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 rB[f] = fma(hz, GzB[f], pv.accB[f]);
                 if (fin) *reinterpret_cast<double2*>(a.nxt.p[f] + go) = make_double2(rA[f], rB[f]);
             }
-            if (!fin) return; // plane 0: `pv` is the ghost plane below (warp-uniform branch)
-            go += SS;
+            if constexpr (!ONEBLOCK)
+            {
+                if (!fin) return; // plane 0: `pv` is the ghost plane below (warp-uniform branch)
+                go += SS;
+            }
+            else
+                go += fin ? SS : 0; // plane 0's dummy pass runs through the same instructions
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2)
             {
@@ -434,9 +505,20 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 K *= 0.5 * irho;
                 const double pr = gm1 * (n[4] - K);
                 const double cs = sqrt_nr2(g * pr * irho);
-                sxm             = pos_max(sxm, fabs(n[1] * irho) + cs);
-                sym             = pos_max(sym, fabs(n[2] * irho) + cs);
-                szm             = pos_max(szm, fabs(n[3] * irho) + cs);
+                const double vx = fabs(n[1] * irho) + cs, vy = fabs(n[2] * irho) + cs, vz = fabs(n[3] * irho) + cs;
+                if constexpr (!ONEBLOCK)
+                {
+                    sxm = pos_max(sxm, vx);
+                    sym = pos_max(sym, vy);
+                    szm = pos_max(szm, vz);
+                }
+                else
+                {
+                    // the dummy pass may produce anything (NaN included): selected away, never compared
+                    sxm = fin ? pos_max(sxm, vx) : sxm;
+                    sym = fin ? pos_max(sym, vy) : sym;
+                    szm = fin ? pos_max(szm, vz) : szm;
+                }
             }
         };
 
@@ -450,7 +532,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 cp_async_commit();
             }
             else
-                zghost(1, gzA, gzB); // in flight during the last plane
+                zghost(1, tab, p, bx, by, gzA, gzB); // in flight during the last plane
             if (sl == 0) mbar_wait(&bar[cst], cph);
             const double* src = ring + cst * C::STAGE + sl * PLD + yy * S + x0 + 2 * xq;
             const int     lo  = (x0 + 2 * xq > 0) ? -1 : 0; // left cell (clamped: replaced by a parked flux)
@@ -469,6 +551,15 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             flux3<2>(pv.A, nw.A, GzA);
             flux3<2>(pv.B, nw.B, GzB);
             finish(pv, GzA, GzB, fin);
+            if constexpr (EARLYZ)
+            {
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    nw.accA[f] = fma(nhz, GzA[f], nw.A.u[f]);
+                    nw.accB[f] = fma(nhz, GzB[f], nw.B.u[f]);
+                }
+            }
             const double2* bfp = reinterpret_cast<const double2*>(sBF) + BUF * 96;
             // ---- x faces
             {
@@ -490,8 +581,8 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                     if (xq == 0) GL[f] = bfl[f];
                     double GR = __shfl_down_sync(0xffffffffu, GL[f], 1);
                     if (xq == 3) GR = bfl[f];
-                    nw.accA[f] = fma(hx, GM[f] - GL[f], nw.A.u[f]);
-                    nw.accB[f] = fma(hx, GR - GM[f], nw.B.u[f]);
+                    nw.accA[f] = fma(hx, GM[f] - GL[f], EARLYZ ? nw.accA[f] : nw.A.u[f]);
+                    nw.accB[f] = fma(hx, GR - GM[f], EARLYZ ? nw.accB[f] : nw.B.u[f]);
                 }
             }
             // ---- y faces
@@ -538,11 +629,14 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 }
             }
             // ---- lower z face
-#pragma unroll
-            for (int f = 0; f < NV; ++f)
+            if constexpr (!EARLYZ)
             {
-                nw.accA[f] = fma(nhz, GzA[f], nw.accA[f]);
-                nw.accB[f] = fma(nhz, GzB[f], nw.accB[f]);
+#pragma unroll
+                for (int f = 0; f < NV; ++f)
+                {
+                    nw.accA[f] = fma(nhz, GzA[f], nw.accA[f]);
+                    nw.accB[f] = fma(nhz, GzB[f], nw.accB[f]);
+                }
             }
             if (!last)
             {
@@ -590,7 +684,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             {
                 if (z == 2)
                 {
-                    resolve_next();
+                    take_next();
                     if (tau_nxt < n_tasks) tab_nxt = tab_load(tau_nxt);
                 }
                 plane_step(z, s0, s1, z > 0, false);
@@ -604,12 +698,18 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             {
                 if (z == 2)
                 {
-                    resolve_next(); // the next task is known by now: request its halo tables
+                    take_next(); // the next task: request its halo tables
                     if (tau_nxt < n_tasks) tab_nxt = tab_load(tau_nxt);
                 }
                 plane_step(z, s0, s1, z > 0, z == S - 1);
                 s0 = s1;
             }
+        }
+        if constexpr (PF)
+        {
+            // the next task's boundary ghosts and ghost plane below: in flight during this task's last
+            // z-face flux and stores (gs now belongs to the next task; sST / sGZ are free since plane S-2)
+            if (tau_nxt < n_tasks) prefetch_task(tau_nxt, tab_nxt);
         }
         // ghost plane above: z-face flux into plane S-1, finish it
         {
@@ -628,10 +728,8 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
         }
         __syncwarp(); // sBF is rewritten by the next task
         ++kc;
-        resolve_next();
         tau_cur = tau_nxt;
         tab     = tab_nxt;
-        if (tau_cur < n_tasks) fetch_next();
     }
 
     if (a.sc.dtmin_out != nullptr)
@@ -660,14 +758,14 @@ template <int S, int CR, int NS, int WPC, int MINB>
 __global__ void __launch_bounds__(WPC * 32, MINB)
 euler3d_dense_kernel_pp(const __grid_constant__ StepArgs a, int n_items)
 {
-    euler3d_dense_body<S, CR, NS, WPC, true>(a, n_items);
+    euler3d_dense_body<S, CR, NS, WPC, kOptPingPong>(a, n_items);
 }
-// occupancy by an explicit register budget (CTA sizes that are not multiples of 128 threads)
-template <int S, int CR, int NS, int WPC, int MAXREG>
-__global__ void __launch_bounds__(WPC * 32) __maxnreg__(MAXREG)
-euler3d_dense_kernel_r(const __grid_constant__ StepArgs a, int n_items)
+// the body's OPT variants (A/B runs)
+template <int S, int CR, int NS, int WPC, int MINB, int OPT>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+euler3d_dense_kernel_o(const __grid_constant__ StepArgs a, int n_items)
 {
-    euler3d_dense_body<S, CR, NS, WPC>(a, n_items);
+    euler3d_dense_body<S, CR, NS, WPC, OPT>(a, n_items);
 }
 
 } // namespace amrb

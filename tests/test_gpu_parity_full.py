@@ -122,8 +122,9 @@ def c3_reference(tmp_path_factory):
 
 
 # storage 1 = interior-only device layout (the C3 bench line), 0 = the reference's padded device layout
-@pytest.mark.parametrize("storage,mode,variant", [(1, 0, 0), (1, 0, 21), (1, 0, 22), (1, 0, 28), (0, 0, 0), (0, 0, 11), (0, 0, 10), (0, 2, 0), (0, 1, 0)],
-                         ids=["dense_bench_kernel", "dense_ring_2x3", "dense_ring_2x2_12warps", "dense_pingpong", "padded_march", "padded_march_1plane", "padded_blockcoop",
+@pytest.mark.parametrize("storage,mode,variant", [(1, 0, 0), (1, 0, 21), (1, 0, 28), (1, 0, 41), (1, 0, 44), (0, 0, 0), (0, 0, 11), (0, 0, 10), (0, 2, 0), (0, 1, 0)],
+                         ids=["dense_bench_kernel", "dense_ring_2x3", "dense_pingpong", "dense_prefetch", "dense_prefetch_oneblock_earlyz",
+                              "padded_march", "padded_march_1plane", "padded_blockcoop",
                               "padded_threadpercell", "padded_unfused"])
 def test_c3_shape_three_levels_matches_reference(amrb, c3_reference, storage, mode, variant):
     g = c3_reference

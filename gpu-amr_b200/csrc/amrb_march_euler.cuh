@@ -77,27 +77,24 @@ __device__ __forceinline__ void prims2(Cell2& c, double g, double gm1)
     c.a = sqrt_nr2(g * c.p * c.ir);
 }
 
-// G = F(L) + F(R) - smax (U_R - U_L): twice the Rusanov flux across a face normal to solver
-// direction DS (0 = x: momentum u[1]; 1 = y: momentum u[2])
+// G = F(L) + F(R) - smax (U_R - U_L): twice the Rusanov flux (EulerPhysics.hpp:74-129) across a face normal to
+// solver direction DS (0 = x: momentum u[1]; 1 = y: momentum u[2]), in WAVE FORM: with F_k = U_k u (+ p for the
+// normal momentum, + p u for the energy) the sum regroups to
+//     G_k = U_k,L (u_L + smax) + U_k,R (u_R - smax)   [+ p_L + p_R]   [+ p_L u_L + p_R u_R]
+// -- 2 DP instructions per component instead of 5 (no per-cell flux vectors, no state differences): 15 per face
+// in 2D, 19 in 3D, where the textbook grouping needs 23 / 29.  Same value up to rounding (one more rounding of
+// rho u against m; parity bound 1e-12); a face's flux is still computed once and used by both cells, so the
+// update telescopes as before.
 template <int DS>
 __device__ __forceinline__ void flux2(const Cell2& L, const Cell2& R, double (&G)[4])
 {
     const double uL = L.u[1 + DS] * L.ir, uR = R.u[1 + DS] * R.ir;
     const double sm = pos_max(fabs(uL) + L.a, fabs(uR) + R.a);
-    G[0]            = (L.u[1 + DS] + R.u[1 + DS]) - sm * (R.u[0] - L.u[0]);
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-    {
-        double fl = L.u[1 + k] * uL, fr = R.u[1 + k] * uR;
-        if (k == DS)
-        {
-            fl += L.p;
-            fr += R.p;
-        }
-        G[1 + k] = (fl + fr) - sm * (R.u[1 + k] - L.u[1 + k]);
-    }
-    const double eL = uL * (L.u[3] + L.p), eR = uR * (R.u[3] + R.p);
-    G[3]            = (eL + eR) - sm * (R.u[3] - L.u[3]);
+    const double wp = uL + sm, wm = uR - sm;
+    G[0]            = fma(R.u[0], wm, L.u[0] * wp);
+    G[1 + DS]       = fma(R.u[1 + DS], wm, fma(L.u[1 + DS], wp, L.p + R.p));
+    G[2 - DS]       = fma(R.u[2 - DS], wm, L.u[2 - DS] * wp);
+    G[3]            = fma(R.u[3], wm, fma(L.u[3], wp, fma(L.p, uL, R.p * uR)));
 }
 
 template <int S, int H, int BAND, int CR, int NS, int WPC>

@@ -84,43 +84,35 @@ __device__ __forceinline__ void prims3(Cell3& c, double g, double gm1)
     c.a = sqrt_nr2(g * c.p * c.ir);
 }
 
-// G = F(L) + F(R) - smax (U_R - U_L) across a face normal to solver direction DS (0 x, 1 y, 2 z)
+// G = F(L) + F(R) - smax (U_R - U_L) across a face normal to solver direction DS (0 x, 1 y, 2 z), in wave form
+// (see flux2, amrb_march_euler.cuh): G_k = U_k,L (u_L + smax) + U_k,R (u_R - smax) [+ pressure terms]
 template <int DS>
 __device__ __forceinline__ void flux3(const Cell3& L, const Cell3& R, double (&G)[5])
 {
     const double uL = L.u[1 + DS] * L.ir, uR = R.u[1 + DS] * R.ir;
     const double sm = pos_max(fabs(uL) + L.a, fabs(uR) + R.a);
-    G[0]            = (L.u[1 + DS] + R.u[1 + DS]) - sm * (R.u[0] - L.u[0]);
+    const double wp = uL + sm, wm = uR - sm;
+    G[0]            = fma(R.u[0], wm, L.u[0] * wp);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-    {
-        double fl = L.u[1 + k] * uL, fr = R.u[1 + k] * uR;
-        if (k == DS)
-        {
-            fl += L.p;
-            fr += R.p;
-        }
-        G[1 + k] = (fl + fr) - sm * (R.u[1 + k] - L.u[1 + k]);
-    }
-    const double eL = uL * (L.u[4] + L.p), eR = uR * (R.u[4] + R.p);
-    G[4]            = (eL + eR) - sm * (R.u[4] - L.u[4]);
+        G[1 + k] = (k == DS) ? fma(R.u[1 + k], wm, fma(L.u[1 + k], wp, L.p + R.p)) : fma(R.u[1 + k], wm, L.u[1 + k] * wp);
+    G[4] = fma(R.u[4], wm, fma(L.u[4], wp, fma(L.p, uL, R.p * uR)));
 }
-
-// same, face normal chosen at run time between x (ds = 0) and y (ds = 1): the lateral boundary
-// faces of a plane are spread over the lanes of one warp
-__device__ __forceinline__ void flux3_xy(const Cell3& L, const Cell3& R, int ds, double (&G)[5])
+// the same across a lateral boundary face of a plane: ghost cell `gc`, interior cell `ic`, face normal x (ds = 0) or
+// y (ds = 1) chosen at run time (the 32 faces of a plane are spread over the lanes of a warp), bsgn = +1 when the
+// ghost cell is the lower one.  G = F(gc) + F(ic) + bsgn smax (U_gc - U_ic), one branch-free form for all sides.
+__device__ __forceinline__ void flux3_bnd(const Cell3& gc, const Cell3& ic, int ds, double bsgn, double (&F)[5])
 {
-    const double mL = ds ? L.u[2] : L.u[1], mR = ds ? R.u[2] : R.u[1];
-    const double uL = mL * L.ir, uR = mR * R.ir;
-    const double sm = pos_max(fabs(uL) + L.a, fabs(uR) + R.a);
-    const double pLx = ds ? 0.0 : L.p, pRx = ds ? 0.0 : R.p;
-    const double pLy = ds ? L.p : 0.0, pRy = ds ? R.p : 0.0;
-    G[0]            = (mL + mR) - sm * (R.u[0] - L.u[0]);
-    G[1]            = (fma(L.u[1], uL, pLx) + fma(R.u[1], uR, pRx)) - sm * (R.u[1] - L.u[1]);
-    G[2]            = (fma(L.u[2], uL, pLy) + fma(R.u[2], uR, pRy)) - sm * (R.u[2] - L.u[2]);
-    G[3]            = (L.u[3] * uL + R.u[3] * uR) - sm * (R.u[3] - L.u[3]);
-    const double eL = uL * (L.u[4] + L.p), eR = uR * (R.u[4] + R.p);
-    G[4]            = (eL + eR) - sm * (R.u[4] - L.u[4]);
+    const double mG = ds ? gc.u[2] : gc.u[1], mI = ds ? ic.u[2] : ic.u[1];
+    const double uG = mG * gc.ir, uI = mI * ic.ir;
+    const double sm = bsgn * pos_max(fabs(uG) + gc.a, fabs(uI) + ic.a);
+    const double wG = uG + sm, wI = uI - sm;
+    const double ps = gc.p + ic.p;
+    F[0]            = fma(ic.u[0], wI, gc.u[0] * wG);
+    F[1]            = fma(ic.u[1], wI, fma(gc.u[1], wG, ds ? 0.0 : ps));
+    F[2]            = fma(ic.u[2], wI, fma(gc.u[2], wG, ds ? ps : 0.0));
+    F[3]            = fma(ic.u[3], wI, gc.u[3] * wG);
+    F[4]            = fma(ic.u[4], wI, fma(gc.u[4], wG, fma(gc.p, uG, ic.p * uI)));
 }
 
 // Restriction of one ghost cell for all 5 fields: mean of the 2^3 fine cells at offset `o`, summed
@@ -478,18 +470,8 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
             }
             prims3(gc, g, gm1);
             prims3(ic_, g, gm1);
-            const int    ds = side >> 1;
-            const double mG = ds ? gc.u[2] : gc.u[1], mI = ds ? ic_.u[2] : ic_.u[1];
-            const double uG = mG * gc.ir, uI = mI * ic_.ir;
-            const double sm = bsgn * pos_max(fabs(uG) + gc.a, fabs(uI) + ic_.a);
-            const double pGx = ds ? 0.0 : gc.p, pIx = ds ? 0.0 : ic_.p;
-            const double pGy = ds ? gc.p : 0.0, pIy = ds ? ic_.p : 0.0;
-            double       F[NV];
-            F[0] = (mG + mI) + sm * (gc.u[0] - ic_.u[0]);
-            F[1] = (fma(gc.u[1], uG, pGx) + fma(ic_.u[1], uI, pIx)) + sm * (gc.u[1] - ic_.u[1]);
-            F[2] = (fma(gc.u[2], uG, pGy) + fma(ic_.u[2], uI, pIy)) + sm * (gc.u[2] - ic_.u[2]);
-            F[3] = (gc.u[3] * uG + ic_.u[3] * uI) + sm * (gc.u[3] - ic_.u[3]);
-            F[4] = (uG * (gc.u[4] + gc.p) + uI * (ic_.u[4] + ic_.p)) + sm * (gc.u[4] - ic_.u[4]);
+            double F[NV];
+            flux3_bnd(gc, ic_, side >> 1, bsgn, F);
             double2* o = reinterpret_cast<double2*>(sBF + ((z & 1) * 32 + lane) * C::BFW);
             o[0]       = make_double2(F[0], F[1]);
             o[1]       = make_double2(F[2], F[3]);

@@ -420,18 +420,8 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             }
             prims3(gc, g, gm1);
             prims3(ic_, g, gm1);
-            const int    ds = side >> 1;
-            const double mG = ds ? gc.u[2] : gc.u[1], mI = ds ? ic_.u[2] : ic_.u[1];
-            const double uG = mG * gc.ir, uI = mI * ic_.ir;
-            const double sm = bsgn * pos_max(fabs(uG) + gc.a, fabs(uI) + ic_.a);
-            const double pGx = ds ? 0.0 : gc.p, pIx = ds ? 0.0 : ic_.p;
-            const double pGy = ds ? gc.p : 0.0, pIy = ds ? ic_.p : 0.0;
-            double       F[NV];
-            F[0] = (mG + mI) + sm * (gc.u[0] - ic_.u[0]);
-            F[1] = (fma(gc.u[1], uG, pGx) + fma(ic_.u[1], uI, pIx)) + sm * (gc.u[1] - ic_.u[1]);
-            F[2] = (fma(gc.u[2], uG, pGy) + fma(ic_.u[2], uI, pIy)) + sm * (gc.u[2] - ic_.u[2]);
-            F[3] = (gc.u[3] * uG + ic_.u[3] * uI) + sm * (gc.u[3] - ic_.u[3]);
-            F[4] = (uG * (gc.u[4] + gc.p) + uI * (ic_.u[4] + ic_.p)) + sm * (gc.u[4] - ic_.u[4]);
+            double F[NV];
+            flux3_bnd(gc, ic_, side >> 1, bsgn, F);
             // parked as [buffer][chunk][face] double2: 16-byte slots of consecutive faces are consecutive in
             // shared memory (the former face-major layout, 48 bytes per face, made lanes 0 / 8 / 16 / 24
             // collide on every store and the two sides of a face pair on every load: 29 % of all shared

@@ -262,9 +262,9 @@ def load_traffic(key):
     p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     try:
         rec = json.load(open(p)).get(key)
-        return (rec.get("dram_bytes_per_launch"), rec.get("source")) if rec else (None, None)
+        return (rec.get("dram_bytes_per_launch"), rec.get("source"), rec.get("patches")) if rec else (None, None, None)
     except Exception:
-        return None, None
+        return None, None, None
 
 
 def pool_field_views(torch, amrb, pool, n_doubles, nvar, which="cur"):
@@ -379,11 +379,11 @@ def measure_single(torch, amrb, wl, args, workload, device, light=False):
     b_alg = 2 * cfg.nvar * 8                                  # read state once + write once, fp64
     kern_ms = ms_total / K   # K back-to-back launches of the fused step (+ init_scalars [+ halo]: < 0.3 %)
     achieved = cells * b_alg / (kern_ms * 1e-3) / 1e9
-    traffic, tsrc = load_traffic(tkey)
-    if tkey == "c3" and traffic:
-        # the capture is of the same kernel on a uniform 8^3 mesh of 262 144 patches: scale to this mesh
-        traffic = traffic * P / 262144.0
-        tsrc = (tsrc or "") + "; scaled by the patch count (%d / 262144)" % P
+    traffic, tsrc, tpatches = load_traffic(tkey)
+    if traffic and tpatches and tpatches != P:
+        # the capture is of the same kernel on a mesh of another size (development runs): scale by the patch count
+        traffic = traffic * P / float(tpatches)
+        tsrc = (tsrc or "") + "; scaled by the patch count (%d / %d)" % (P, tpatches)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tsrc,
                 "kernel": kernel, "kernel_ms": kern_ms,

@@ -74,7 +74,9 @@ struct DenseInst
             // 2 stages (8^3) / 1-plane cp.async chunks, 4 stages (16^3); 21 = 2-plane chunks, 3 stages;
             // 28 = two planes per loop trip; 41 / 44 = body options (amrb_march_euler3d_dense.cuh: kOpt*); all within
             // 1 % of variant 0 (profiles/r02_summary.md).  Earlier A/B runs, removed again: 3 CTAs per SM with 2-plane
-            // chunks, 9 / 10 / 12 warps per SM under __maxnreg__ (slower: spills), one CTA per SM (5.29 vs 3.53 ms)
+            // chunks, 9 / 10 / 12 warps per SM under __maxnreg__ (slower: spills), one CTA per SM (5.29 vs 3.53 ms), parked
+            // fluxes loaded by the boundary lanes only (equal), lateral ghost gathers of ONE field instead of five (a wrong-
+            // result probe of what the per-lane cp.async gathers cost: 3.47 -> 3.08 ms)
             if constexpr (S == 8)
             {
                 if (a.variant == 21)

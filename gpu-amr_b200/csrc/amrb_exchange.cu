@@ -7,9 +7,10 @@
 //                        done, after a system-scope fence -- drops this rank's CFL minimum into every peer's
 //                        mailbox and raises its arrival flag there (pack + send + signal fused);
 //
-// followed on the receiving side by exchange_wait_kernel (one warp: acquire-spins on the peers' flags, folds
-// their CFL minima into this rank's dt-min slot = the all-reduce(min)) and the local unpack into the ghost
-// slots.  Receive buffers and mailbox slots are double-buffered by generation parity: a peer can be at most
+// followed on the receiving side by exchange_unpack_kernel: acquire-spin on the peers' flags, fold of their CFL
+// minima into this rank's dt-min slot (= the all-reduce(min)) and the unpack into the ghost slots in one launch
+// (exchange_wait_kernel + the pool's unpack kernel do the same in two launches: overlapped schedule, per-phase
+// timing, drivers that hold several ranks in one process).  Receive buffers and mailbox slots are double-buffered by generation parity: a peer can be at most
 // one exchange ahead (its next push needs this rank's push of the current generation).  The K-step batch
 // loop lives here, in C++ (amrb_exchange_advance_batch_async): nothing on the host runs between two steps.
 //
@@ -97,15 +98,21 @@ __global__ void __launch_bounds__(128) face_push_kernel(const __grid_constant__ 
             out[it] = a.cur.p[f][(size_t)p * a.stored + gl];
         }
     }
-    // ---- completion: the last CTA to finish signals every peer
-    __threadfence_system();
+    // ---- completion: the last CTA to finish signals every peer.  One system-scope fence per CTA, by the thread
+    // that counts the CTA in after the block barrier (the barrier orders the other threads' remote stores before
+    // it: the cooperative-groups grid-barrier pattern); 128 fences per CTA made the kernel wait 128 times for the
+    // NVLink acknowledgements
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(a.done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        last = (atomicAdd(a.done, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (!last) return;
-    __threadfence_system();
     if (threadIdx.x < a.world && threadIdx.x != a.rank && a.peer_box[threadIdx.x] != nullptr)
     {
+        __threadfence_system();
         Mailbox* box = a.peer_box[threadIdx.x];
         if (a.tgen != 0)
         {
@@ -152,6 +159,92 @@ __global__ void exchange_wait_kernel(Mailbox* box, int world, int rank, unsigned
         v                          = t < v ? t : v;
     }
     if (lane == 0 && my_dtmin != nullptr) *my_dtmin = v;
+}
+
+// wait + all-reduce(min) fold + unpack in ONE launch (the plain schedule's receiving side): every CTA's first warp
+// acquire-spins on the peers' data flags of this generation, CTA 0 also on the CFL-minimum flags and folds the
+// minima into this rank's dt-min slot; then the CTA copies its entry's slab from the receive buffer (read past
+// L1: the lines are written by the peers) into the ghost slot.  Same slab layout as face_push_kernel.
+struct UnpackArgs
+{
+    FieldPtrs           cur;
+    const int32_t*      entries; // [count][2] = {ghost slot, direction}
+    int                 count;
+    const double*       buffer;  // my receive buffer of this generation
+    Mailbox*            box;
+    int                 world, rank;
+    unsigned long long  gen, tgen;
+    unsigned long long* my_dtmin; // may be null: no CFL minimum in this exchange
+    int*                timed_out;
+    long long           timeout_cycles;
+    int                 R, S, HS, NV, T, stored;
+};
+__global__ void __launch_bounds__(128) exchange_unpack_kernel(const __grid_constant__ UnpackArgs a)
+{
+    if (threadIdx.x < 32)
+    {
+        const int          lane = threadIdx.x;
+        const bool         fold = (blockIdx.x == 0) && a.my_dtmin != nullptr;
+        unsigned long long v    = ~0ull;
+        if (lane < a.world && lane != a.rank)
+        {
+            const long long t0 = clock64();
+            bool            ok = true;
+            while (ld_acquire_sys(&a.box->flag[lane]) < a.gen || (fold && ld_acquire_sys(&a.box->tflag[lane]) < a.tgen))
+            {
+                if (clock64() - t0 > a.timeout_cycles)
+                {
+                    ok = false;
+                    break;
+                }
+                __nanosleep(64);
+            }
+            if (!ok)
+                atomicExch(a.timed_out, 1);
+            else if (fold)
+                v = a.box->dtmin[a.tgen & 1][lane];
+        }
+        else if (lane == a.rank && fold)
+            v = *a.my_dtmin;
+        if (fold)
+        {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+                v                          = t < v ? t : v;
+            }
+            if (lane == 0) *a.my_dtmin = v;
+        }
+    }
+    __syncthreads();
+    const int e = blockIdx.x;
+    if (e >= a.count) return;
+    const int     p = a.entries[2 * e], d = a.entries[2 * e + 1];
+    const int     dim = d >> 1, pos = d & 1;
+    const int     P    = a.S + 2 * a.HS;
+    const int     face = (a.R == 2) ? a.S : a.S * a.S;
+    const int     slab = a.T * face;
+    const double* in   = a.buffer + (size_t)e * a.NV * slab;
+    for (int it = threadIdx.x; it < a.NV * slab; it += blockDim.x)
+    {
+        const int f = it / slab, r = it % slab, layer = r / face;
+        int       t = r % face, gl = 0, pitch = 1;
+        for (int k = a.R - 1; k >= 0; --k)
+        {
+            int i;
+            if (k == dim)
+                i = pos ? (a.HS + a.S - 1 - layer) : (a.HS + layer);
+            else
+            {
+                i = a.HS + (t % a.S);
+                t /= a.S;
+            }
+            gl += i * pitch;
+            pitch *= P;
+        }
+        a.cur.p[f][(size_t)p * a.stored + gl] = __ldcg(in + it);
+    }
 }
 } // namespace
 
@@ -241,6 +334,36 @@ amrb_status wait_and_unpack(amrb_exchange* ex, unsigned long long* dtmin_slot)
         if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("face unpack: ") + cudaGetErrorString(e));
         ++ex->launches;
     }
+    return AMRB_OK;
+}
+
+// the same in one launch (exchange_unpack_kernel)
+amrb_status wait_unpack_fused(amrb_exchange* ex, unsigned long long* dtmin_slot)
+{
+    amrb_pool* p = ex->pool;
+    UnpackArgs a{};
+    a.cur            = p->cur;
+    a.entries        = ex->d_recv;
+    a.count          = (int)ex->n_recv;
+    a.buffer         = ex->recv[ex->gen & 1];
+    a.box            = ex->box;
+    a.world          = ex->world;
+    a.rank           = ex->rank;
+    a.gen            = ex->gen;
+    a.tgen           = ex->tgen;
+    a.my_dtmin       = dtmin_slot;
+    a.timed_out      = ex->h_timeout;
+    a.timeout_cycles = 8000000000ll; // ~4 s at 2 GHz: a peer that died must not hang this GPU
+    a.R              = p->lay.rank;
+    a.S              = p->lay.size[0];
+    a.HS             = p->dense ? 0 : p->lay.halo;
+    a.NV             = p->lay.nvar;
+    a.T              = std::min(2 * p->lay.halo, p->lay.size[0]);
+    a.stored         = (int)p->flat;
+    exchange_unpack_kernel<<<(unsigned)std::max<size_t>(ex->n_recv, 1), 128, 0, p->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AMRB_ERR_CUDA, std::string("exchange_unpack_kernel: ") + cudaGetErrorString(e));
+    ++ex->launches;
     return AMRB_OK;
 }
 } // namespace
@@ -417,8 +540,8 @@ amrb_status amrb_exchange_set_lists(amrb_exchange* ex, const int32_t* boundary, 
 }
 
 // amr_solver::advance_batch_async (solver/amr_solver.hpp:155-243) over the sharded mesh.
-//   plain schedule (overlap = 0):  per step push (slabs + CFL minimum + flags), wait (+ all-reduce(min) fold),
-//       unpack, the fused step over all owned patches;
+//   plain schedule (overlap = 0):  per step push (slabs + CFL minimum + flags), wait + all-reduce(min) fold +
+//       unpack (one launch; three when per-phase timing is on), the fused step over all owned patches;
 //   overlapped schedule (overlap = 1, needs amrb_exchange_set_lists): per step wait + unpack, the fused step over
 //       the BOUNDARY patches, then -- on a side stream, under the launch over the INTERIOR patches -- the slab push
 //       of the next step straight from the next buffer; the CFL minimum follows in a push of its own once both
@@ -449,7 +572,9 @@ amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, d
         {
             s = push(ex, slot(k));
             if (ex->timing) cudaEventRecord(ex->tev[4 * k + 1], p->stream);
-            if (s == AMRB_OK)
+            if (s == AMRB_OK && !ex->timing)
+                s = wait_unpack_fused(ex, slot(k));
+            else if (s == AMRB_OK)
             {
                 // wait and unpack timed separately
                 exchange_wait_kernel<<<1, 32, 0, p->stream>>>(ex->box, ex->world, ex->rank, ex->gen, ex->tgen, slot(k),
@@ -498,7 +623,7 @@ amrb_status amrb_exchange_advance_batch_async(amrb_exchange* ex, size_t steps, d
             s = fail(AMRB_ERR_CUDA, "cudaStreamWaitEvent");
     }
     if (s == AMRB_OK) s = push(ex, nullptr);
-    if (s == AMRB_OK) s = wait_and_unpack(ex, nullptr);
+    if (s == AMRB_OK) s = ov ? wait_and_unpack(ex, nullptr) : wait_unpack_fused(ex, nullptr);
     if (s != AMRB_OK)
     {
         p->batch_open   = false;

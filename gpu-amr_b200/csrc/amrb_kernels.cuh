@@ -1046,9 +1046,12 @@ interior_copy_kernel(double* __restrict__ padded, double* __restrict__ dense, in
 }
 
 // ---- inter-GPU ghost faces -----------------------------------------------------------------------------
-// entry e = {patch, direction}; slab = the T = min(2H, S) interior layers next to face `direction`,
+// entry e = {patch, direction | layers << 4}; slab = the T = min(2H, S) interior layers next to face `direction`,
 // every field (a finer neighbor restricts 2 fine layers per coarse ghost layer, patch_utils.hpp:
-// 334-386, so 2H layers cover all three halo operators); buffer layout [entry][field][layer][face cell]
+// 334-386, so 2H layers cover all three halo operators); buffer layout [entry][field][layer][face cell].
+// `layers` (0 = all T) is how many of them are moved: H are enough when no COARSER patch reads this face
+// (same-level copy and injection into a finer patch look at the first H layers only) -- on a mostly uniform
+// mesh that halves the bytes on the wire; the slab keeps its fixed size and layout.
 template <int R, int S, int H>
 struct SlabGeo
 {
@@ -1064,12 +1067,13 @@ face_pack_kernel(FieldPtrs cur, const int32_t* __restrict__ entries, int count,
     using G     = Geo<R, S, H, HS>;
     const int e = blockIdx.x;
     if (e >= count) return;
-    const int     p = entries[2 * e], d = entries[2 * e + 1];
+    const int     p = entries[2 * e], dw = entries[2 * e + 1], d = dw & 15;
     const int     dim = d >> 1, pos = d & 1;
     constexpr int SLAB = SlabGeo<R, S, H>::SLAB;
-    for (int it = threadIdx.x; it < NV * SLAB; it += blockDim.x)
+    const int     part = ((dw >> 4) > 0 && (dw >> 4) < SlabGeo<R, S, H>::T) ? (dw >> 4) * G::FACE : SLAB;
+    for (int i2 = threadIdx.x; i2 < NV * part; i2 += blockDim.x)
     {
-        const int f = it / SLAB, r = it % SLAB, layer = r / G::FACE;
+        const int f = i2 / part, r = i2 % part, layer = r / G::FACE, it = f * SLAB + r;
         int       t = r % G::FACE, gl = 0;
 #pragma unroll
         for (int k = R - 1; k >= 0; --k)

@@ -22,7 +22,7 @@ from . import binding as B
 class ShardPlan:
     """Who owns what, which ghost slots exist, and the pack / unpack entry lists."""
 
-    def __init__(self, levels, rel, nbr, quad, rank, world, slab_layers_ok=True):
+    def __init__(self, levels, rel, nbr, quad, rank, world, slab_layers_ok=True, halo_layers=None):
         P = len(levels)
         self.rank, self.world, self.P = rank, world, P
         ndir, kf = nbr.shape[1], nbr.shape[2]
@@ -55,8 +55,16 @@ class ShardPlan:
         J = nbr[I, D, K].astype(np.int64)
         cross = owner[I] != owner[J]
         I, D, J = I[cross], D[cross], J[cross]
-        ent = np.unique(np.stack([owner[J].astype(np.int64), owner[I].astype(np.int64), J, D ^ 1],
-                                 axis=1), axis=0)             # src rank, dst rank, patch, face
+        ent, inv = np.unique(np.stack([owner[J].astype(np.int64), owner[I].astype(np.int64), J, D ^ 1],
+                                      axis=1), axis=0, return_inverse=True)   # src rank, dst rank, patch, face
+        # layers on the wire (entry word = face | layers << 4): all min(2h, S) of them only when a COARSER patch
+        # reads the face (restriction of 2h fine layers); same-level copies and injection into finer patches
+        # look at the first h layers
+        lv = np.asarray(levels)
+        coarser_reader = np.zeros(len(ent), dtype=bool)
+        np.logical_or.at(coarser_reader, inv.reshape(-1), lv[I] < lv[J])
+        if slab_layers_ok and halo_layers is not None:
+            ent[:, 3] |= np.where(coarser_reader, 0, halo_layers).astype(np.int64) << 4
         snd = ent[ent[:, 0] == rank]
         snd = snd[np.lexsort((snd[:, 3], snd[:, 2], snd[:, 1]))]
         rcv = ent[ent[:, 1] == rank]
@@ -164,7 +172,7 @@ class ShardedSolver:
         self.ex = None
         self._peer_maps = []
         levels, rel, nbr, quad = host_tree.tables()
-        self.plan = pl = ShardPlan(levels, rel, nbr, quad, rank, world)
+        self.plan = pl = ShardPlan(levels, rel, nbr, quad, rank, world, halo_layers=cfg.halo)
         self.ids = host_tree.ids()[pl.lo:pl.hi]
         self.lay = B.make_layout(cfg.rank, cfg.size, cfg.halo, cfg.eq, cfg.depth, storage)
         # capacity: slots for owned + ghost patches; meshes that change need headroom
@@ -309,7 +317,7 @@ class ShardedSolver:
         if len(kind):
             self.pool.apply_plan(kind, src, child)
         levels, rel, nbr, quad = new_host_tree.tables()
-        self.plan = pl = ShardPlan(levels, rel, nbr, quad, self.rank, self.world)
+        self.plan = pl = ShardPlan(levels, rel, nbr, quad, self.rank, self.world, halo_layers=self.cfg.halo)
         if pl.n_total > self.capacity or rp.staging_slots(self.rank) > self.capacity:
             raise B.AmrbError("shard of %d patches (+ghosts) exceeds the pool capacity %d"
                               % (pl.n_total, self.capacity))

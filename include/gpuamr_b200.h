@@ -236,7 +236,10 @@ double*     amrb_pool_dtmin_slot(amrb_pool* pool, size_t k);
  *    pack: gathers, for each (patch, direction) entry, the min(2h, S)-thick interior slab next to
  *    that face of every field (covers the same / coarser / finer halo operators) into a contiguous
  *    send buffer; unpack: scatters a received buffer into the same slab of a ghost slot.
- *    Entry = {int32 patch, int32 direction}; buffer = [entry][field][layer][face cell].
+ *    Entry = {int32 patch, int32 direction | layers << 4}; buffer = [entry][field][layer][face cell].
+ *    layers = how many of the slab's layers are moved (0 = all min(2h, S)); h are enough for a face no
+ *    COARSER patch reads (same-level copy and injection into a finer patch use the first h layers only).
+ *    The slab keeps its fixed size and layout either way.
  * ---------------------------------------------------------------------------------------- */
 size_t      amrb_pool_face_slab_doubles(const amrb_pool* pool, int direction); /* per field */
 amrb_status amrb_pool_pack_faces(amrb_pool* pool, const int32_t* dev_entries, size_t count,

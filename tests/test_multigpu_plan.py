@@ -68,6 +68,33 @@ def test_plans_are_mutually_consistent(amrb, world, cfgname):
         assert need == set(map(tuple, p.recv_entries.tolist()))
 
 
+@pytest.mark.parametrize("cfgname", ["r2_s8_h1_d7_euler", "r3_s4_h1_d5_euler"])
+def test_layers_on_the_wire(amrb, cfgname):
+    """entry word = face | layers << 4: all min(2h, S) layers (0) exactly for the faces a COARSER patch reads,
+    h layers otherwise; both sides of every pair compute the same word"""
+    mg = importlib.import_module("gpu-amr_b200.multigpu")
+    cfg, t = _tree(amrb, cfgname)
+    levels, rel, nbr, quad = t.tables()
+    world = 3
+    plans = [mg.ShardPlan(levels, rel, nbr, quad, r, world, halo_layers=cfg.halo) for r in range(world)]
+    full = part = 0
+    for r, p in enumerate(plans):
+        so = np.concatenate([[0], np.cumsum(p.send_counts)])
+        for q, pq in enumerate(plans):
+            ro = np.concatenate([[0], np.cumsum(pq.recv_counts)])
+            assert np.array_equal(p.send_global[so[q]:so[q + 1]], pq.recv_global[ro[r]:ro[r + 1]])
+        glob = np.concatenate([np.arange(p.lo, p.hi), p.ghost_global])       # local slot -> global patch
+        for slot, word in p.recv_entries.tolist():
+            j, face, layers = int(glob[slot]), word & 15, word >> 4
+            readers = [i for i in range(p.lo, p.hi) if j in nbr[i, face ^ 1]]
+            assert readers, (j, face)
+            coarser = any(levels[i] < levels[j] for i in readers)
+            assert layers == (0 if coarser else cfg.halo), (j, face, layers, coarser)
+            full += coarser
+            part += not coarser
+    assert full > 0 and part > 0
+
+
 def _worker(rank, world, port, cfgname, q):
     import torch
     import torch.distributed as dist

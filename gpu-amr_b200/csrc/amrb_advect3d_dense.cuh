@@ -14,8 +14,13 @@
 //   * a lane owns two x-adjacent cells; the x-neighbors are the adjacent lanes' cells (warp shuffles), the
 //     y-neighbors come from the staged plane; stores are 16-byte pairs, 512 contiguous bytes per warp
 //     instruction, every sector fully written.
-// Arithmetic: AdvectionPhysics.hpp:45-66 (Rusanov), amr_solver.hpp:265-353 (update order), expression for
-// expression the thread-per-cell step_kernel (amrb_kernels.cuh).
+//   * UPWIND form of the Rusanov flux: for the reference's constant velocity v = {1, 0.5, 0} >= 0
+//     (AdvectionPhysics.hpp:24, 45-66)  F = 1/2 (v uL + v uR) - 1/2 |v| (uR - uL) = v uL: the downwind cell
+//     cancels.  The kernel evaluates v uL directly -- the result differs from the textbook grouping by the rounding
+//     of that cancellation (~1e-16 of the field, parity bound 1e-12) -- and therefore never reads the x+ / y+
+//     ghost cells: half of the lateral gathers, each of which is one 8-byte element per cache line on the x
+//     sides (profiles/r02_summary.md: those gathers, not the 4 KB stream, are what the kernel waits for).
+// Arithmetic: AdvectionPhysics.hpp:45-66 (Rusanov), amr_solver.hpp:265-353 (update order).
 #pragma once
 #include "amrb_march_euler3d.cuh"
 
@@ -31,7 +36,7 @@ struct Adv3DenseCfg
     static constexpr int ZT    = TASK / SS;      // planes per task
     static constexpr int NB    = S / ZT;         // tasks per patch
     static constexpr int HP    = S / 2;          // pairs per row
-    static constexpr int GH    = 4 * S * ZT;     // ghost cells per task: [side][plane][tangential]
+    static constexpr int GH    = 2 * S * ZT;     // upwind ghost cells per task: [side x- / y-][plane][tangential]
     static constexpr int WARP_DOUBLES = 2 * TASK + 2 * GH;
     static constexpr size_t SMEM      = (size_t)WPC * WARP_DOUBLES * sizeof(double);
     static_assert(S == 8 || S == 16, "512-cell tasks of whole planes");
@@ -98,8 +103,8 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
 #pragma unroll
         for (int e = lane; e < GH; e += 32)
         {
-            const int sd = e / (S * ZT), r = e % (S * ZT), zl = r / S, t = r % S;
-            const int d  = (sd < 2) ? 4 + sd : sd;      // tree direction: x-, x+, y-, y+
+            const int sd = e / (S * ZT), r = e % (S * ZT), zl = r / S, t = r % S; // sd: 0 = x-, 1 = y-
+            const int d  = sd ? 2 : 4;                  // tree direction of the side
             const int m  = tab_meta3(tab, p, d);
             const int rel = m & 3;
             const int z   = z0 + zl;
@@ -108,17 +113,7 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
             const int nq   = __shfl_sync(0xffffffffu, tab, d * 4 + nsel);
             // interior coordinates of the ghost cell mirrored into the neighbor's frame
             // (patch_utils.hpp:322-327): the normal coordinate -1 -> S-1, S -> 0
-            int fy, fx;
-            if (sd < 2)
-            {
-                fy = t;
-                fx = (sd & 1) ? 0 : S - 1;
-            }
-            else
-            {
-                fx = t;
-                fy = (sd & 1) ? 0 : S - 1;
-            }
+            const int fy = sd ? S - 1 : t, fx = sd ? t : S - 1;
             if (rel == 2)
             {
                 // finer_t: mean of the 2^3 fine cells of one of the 4 finer neighbors, summed
@@ -144,8 +139,8 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
                 // own boundary cell.  One select per coordinate instead of a branch per relation.
                 const int  qz = (m >> 2) & 1, qy = (m >> 3) & 1, qx = (m >> 4) & 1;
                 const bool co = (rel == 3), none = (rel == 0);
-                const int  iy = (sd < 2) ? t : ((sd & 1) ? S - 1 : 0);
-                const int  ix = (sd < 2) ? ((sd & 1) ? S - 1 : 0) : t;
+                const int  iy = sd ? 0 : t;
+                const int  ix = sd ? t : 0;
                 const int  sz = co ? qz * HF + z / 2 : z;
                 const int  sy = co ? qy * HF + fy / 2 : (none ? iy : fy);
                 const int  sx = co ? qx * HF + fx / 2 : (none ? ix : fx);
@@ -195,49 +190,25 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
             const int x2 = q % HP, y = (q / HP) % S, zl = q / (HP * S);
             const int o  = zl * SS + y * S + 2 * x2;
             const double2 c = *reinterpret_cast<const double2*>(pl + o);
-            const double  gl = gh[(0 * ZT + zl) * S + y], gr = gh[(1 * ZT + zl) * S + y];
-            const double  sl = __shfl_up_sync(0xffffffffu, c.y, 1), sr = __shfl_down_sync(0xffffffffu, c.x, 1);
-            const double  lft = (x2 == 0) ? gl : sl, rgt = (x2 == HP - 1) ? gr : sr;
-            const double* pdn = (y > 0) ? pl + o - S : gh + (2 * ZT + zl) * S + 2 * x2;
-            const double* pup = (y < S - 1) ? pl + o + S : gh + (3 * ZT + zl) * S + 2 * x2;
-            const double2 dn = *reinterpret_cast<const double2*>(pdn);
-            const double2 up = *reinterpret_cast<const double2*>(pup);
-            double2 r;
+            const double  gl  = gh[(0 * ZT + zl) * S + y];
+            const double  sl  = __shfl_up_sync(0xffffffffu, c.y, 1);
+            const double  lft = (x2 == 0) ? gl : sl;
+            const double* pdn = (y > 0) ? pl + o - S : gh + (1 * ZT + zl) * S + 2 * x2;
+            const double2 dn  = *reinterpret_cast<const double2*>(pdn);
+            // U - cx (F(U) - F(left)) - cy (G(U) - G(below)),  F = 1.0 u, G = 0.5 u  (update order of amr_solver.hpp:330)
+            constexpr double vx = 1.0, vy = 0.5;
+            double2          r;
             {
-                // cell A: left = lft, right = c.y
-                const double u = c.x;
-                double       upd = 0.0;
-                {
-                    const double v = 1.0, uL = lft, uR = c.y;
-                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                    upd -= cx * (fR - fL);
-                }
-                {
-                    const double v = 0.5, uL = dn.x, uR = up.x;
-                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                    upd -= cy * (fR - fL);
-                }
-                r.x = u + upd;
+                double upd = 0.0;
+                upd -= cx * (vx * c.x - vx * lft);
+                upd -= cy * (vy * c.x - vy * dn.x);
+                r.x = c.x + upd;
             }
             {
-                // cell B: left = c.x, right = rgt
-                const double u = c.y;
-                double       upd = 0.0;
-                {
-                    const double v = 1.0, uL = c.x, uR = rgt;
-                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                    upd -= cx * (fR - fL);
-                }
-                {
-                    const double v = 0.5, uL = dn.y, uR = up.y;
-                    const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                    const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                    upd -= cy * (fR - fL);
-                }
-                r.y = u + upd;
+                double upd = 0.0;
+                upd -= cx * (vx * c.y - vx * c.x);
+                upd -= cy * (vy * c.y - vy * dn.y);
+                r.y = c.y + upd;
             }
             *reinterpret_cast<double2*>(out + o) = r;
         }

@@ -180,8 +180,8 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
             nq.v[0] = tab_get(tb, j * 10 + 2 * d);
             nq.v[1] = tab_get(tb, j * 10 + 2 * d + 1);
             if (g >= np * GP) continue;
-            if (sd == 2 && r0 != 0) continue;          // the band does not touch the bottom / top face
-            if (sd == 3 && r0 + BR != S) continue;
+            if (sd & 1) continue;                      // x+ / y+: never read (upwind form, see the compute loop)
+            if (sd == 2 && r0 != 0) continue;          // the band does not touch the bottom face
             if ((m & 3) == 0) continue;
             int idx[2];
             if (sd < 2)
@@ -240,8 +240,8 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
                 const int d = (sd < 2) ? 2 + sd : sd - 2;
                 const int m = (tab_get(tab_cur, j * 10 + 8) >> (8 * d)) & 0xff;
                 if (g >= np * GP) continue;
+                if (sd & 1) continue;
                 if (sd == 2 && r0 != 0) continue;
-                if (sd == 3 && r0 + BR != S) continue;
                 if ((m & 3) == 0) continue;
                 int o;
                 if (sd < 2)
@@ -252,7 +252,11 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
             }
         }
         __syncwarp();
-        // ---- compute: every element of the padded interior rows (ghost columns = copy of the adjacent cell)
+        // ---- compute: every element of the padded interior rows (ghost columns = copy of the adjacent cell).
+        // UPWIND form of the Rusanov flux: for the reference's constant velocity v = {1, 0.5} >= 0
+        // (AdvectionPhysics.hpp:24, 45-66)  F = 1/2 (v uL + v uR) - 1/2 |v| (uR - uL) = v uL; the kernel evaluates
+        // v uL directly (differs from the textbook grouping by the rounding of that cancellation, ~1e-16 of the
+        // field; parity bound 1e-12) and never reads the x+ / y+ ghost cells: half of the gathers.
         for (int j = 0; j < np; ++j)
         {
             const int    p   = patch_of(item0 + j);
@@ -274,27 +278,16 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
                     const bool first = (pc == 0), last = (pc == HP - 1);
                     const double2 ct = *reinterpret_cast<const double2*>(tile + o);
                     const double2 dn = *reinterpret_cast<const double2*>(tile + o - P);
-                    const double2 up = *reinterpret_cast<const double2*>(tile + o + P);
                     const double  lf = tile[first ? o : o - 1];
-                    const double  rg = tile[last ? o + 1 : o + 2];
+                    constexpr double vx = 1.0, vy = 0.5;
                     double nv[2];
 #pragma unroll
                     for (int s2 = 0; s2 < 2; ++s2)
                     {
-                        const double u = s2 ? ct.y : ct.x;
+                        const double u = s2 ? ct.y : ct.x, uL = s2 ? ct.x : lf, uD = s2 ? dn.y : dn.x;
                         double       upd = 0.0;
-                        {
-                            const double v = 1.0, uL = s2 ? ct.x : lf, uR = s2 ? rg : ct.y;
-                            const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                            const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                            upd -= cx * (fR - fL);
-                        }
-                        {
-                            const double v = 0.5, uL = s2 ? dn.y : dn.x, uR = s2 ? up.y : up.x;
-                            const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                            const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                            upd -= cy * (fR - fL);
-                        }
+                        upd -= cx * (vx * u - vx * uL);
+                        upd -= cy * (vy * u - vy * uD);
                         nv[s2] = u + upd;
                     }
                     *reinterpret_cast<double2*>(out + r * P + c) = make_double2(first ? nv[1] : nv[0], last ? nv[0] : nv[1]);
@@ -307,20 +300,11 @@ advect2d_kernel(const __grid_constant__ StepArgs a, int n_items)
                 {
                     const int    cc = min(max(c, H), H + S - 1);
                     const int    o  = (C::ROW0 + r) * P + cc;
-                    const double u  = tile[o];
-                    double       upd = 0.0;
-                    {
-                        const double v = 1.0, uL = tile[o - 1], uR = tile[o + 1];
-                        const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                        const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                        upd -= cx * (fR - fL);
-                    }
-                    {
-                        const double v = 0.5, uL = tile[o - P], uR = tile[o + P];
-                        const double fL = 0.5 * (uL * v + u * v) - 0.5 * fabs(v) * (u - uL);
-                        const double fR = 0.5 * (u * v + uR * v) - 0.5 * fabs(v) * (uR - u);
-                        upd -= cy * (fR - fL);
-                    }
+                    constexpr double vx = 1.0, vy = 0.5;
+                    const double     u = tile[o];
+                    double           upd = 0.0;
+                    upd -= cx * (vx * u - vx * tile[o - 1]);
+                    upd -= cy * (vy * u - vy * tile[o - P]);
                     out[e] = u + upd;
                     r += 32 / P;
                     c += 32 % P;

@@ -203,13 +203,12 @@ struct Inst
         {
             if constexpr (R == 2)
             {
-                // warp-autonomous streaming kernel (amrb_advect2d.cuh).  variant 10 = thread per cell;
-                // 41 / 42 = 8- / 16-row bands of the streaming kernel for wide patches (default: patches
-                // wider than 16 cells keep the thread-per-cell kernel, narrower ones stream in groups)
-                // measured (profiles/r02i_dev_bench.jsonl): 64-wide patches 0.59 thread per cell vs 0.57 streamed;
-                // 32-wide 0.37 vs 0.43 (16-row bands); narrower patches stream in groups (0.18 - 0.39 vs 0.09)
-                const bool wide = (S > 32);
-                if (a.variant != 10 && (!wide || a.variant == 41 || a.variant == 42))
+                // warp-autonomous streaming kernel (amrb_advect2d.cuh), upwind form: narrow patches stream in groups
+                // of whole patches, patches of 32 cells and wider in 16-row bands.  variant 10 = the thread-per-cell
+                // kernel, 41 = 8-row bands.  Measured (profiles/r02z_dev_bench.jsonl, fraction of the HBM roofline):
+                // 64-wide 0.75 (16-row bands) / 0.68 (8-row) / 0.60 (thread per cell); 32-wide 0.58; 16-wide 0.44;
+                // 10 x 10 / halo 2 (the C1 shape) 0.27; before the upwind form: 0.57 / - / 0.59, 0.43, 0.39, 0.22
+                if (a.variant != 10)
                 {
                     auto launch = [&](auto kern, size_t smem, int tasks, int wpc, int ctas) {
                         static DevicePrepared prepared;
@@ -217,7 +216,7 @@ struct Inst
                         const int grid = std::max(1, std::min(sm_count() * ctas, (tasks + wpc - 1) / wpc));
                         kern<<<grid, wpc * 32, smem, st>>>(a, n_items);
                     };
-                    if ((wide && a.variant == 42) || (S == 32 && a.variant != 41))
+                    if (S >= 32 && a.variant != 41)
                     {
                         using AC = Adv2Cfg<S, H, 4, (S % 16 == 0 ? 16 : 8)>;
                         launch(advect2d_kernel<S, H, 4, 2, (S % 16 == 0 ? 16 : 8)>, AC::SMEM, n_items * AC::NB, 4, 2);

@@ -71,7 +71,7 @@ def test_device_matches_reference_dump(amrb, name, mode):
 
 
 @pytest.mark.parametrize("storage", [0, 1], ids=["padded", "interior"])
-@pytest.mark.parametrize("cfgname,levels", [("r2_s64_h1_d7_euler", 2), ("r2_s32_h1_d7_adv", 2),
+@pytest.mark.parametrize("cfgname,levels", [("r2_s64_h1_d7_euler", 2), ("r2_s32_h1_d7_adv", 2), ("r2_s64_h1_d7_adv", 2),
                                             ("r3_s16_h1_d5_euler", 1), ("r3_s8_h1_d5_euler", 2),
                                             ("r3_s8_h1_d5_adv", 2), ("r3_s16_h1_d5_adv", 1),
                                             ("r2_s10_h2_d7_euler", 2)])

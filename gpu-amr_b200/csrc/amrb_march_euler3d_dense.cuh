@@ -54,9 +54,6 @@ struct March3DenseCfg
 // next-step wave speeds of plane 0's dummy pass are computed and discarded instead of branched around);
 // 8 = the lower z-face flux enters the accumulators first (10 fewer doubles live across the x / y faces)
 constexpr int kOptPingPong = 1, kOptPrefetch = 2, kOptOneBlock = 4, kOptEarlyZ = 8;
-// experiments: 16 = gather only field 0 of the lateral ghost cells (WRONG results: measures what the per-lane
-// cp.async gathers cost); 32 = parked boundary fluxes loaded by the lanes that use them only
-constexpr int kOptFewGhost = 16, kOptPredPark = 32;
 
 template <int S, int CR, int NS, int WPC, int OPT = 0>
 __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_items)
@@ -65,8 +62,6 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
     constexpr bool PF       = (OPT & kOptPrefetch) != 0;
     constexpr bool ONEBLOCK = (OPT & kOptOneBlock) != 0;
     constexpr bool EARLYZ   = (OPT & kOptEarlyZ) != 0;
-    constexpr int  NGH      = (OPT & kOptFewGhost) ? 1 : 5;
-    constexpr bool PREDPARK = (OPT & kOptPredPark) != 0;
     using C           = March3DenseCfg<S, CR, NS, WPC>;
     constexpr int NV  = 5;
     constexpr int SS  = C::SS;
@@ -285,7 +280,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
         {
             const size_t o = (size_t)gs.q0 * N + (size_t)(gs.zbase + (z >> gs.zshift)) * SS + gs.off;
 #pragma unroll
-            for (int f = 0; f < NGH; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
+            for (int f = 0; f < NV; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
         }
     };
     // source of the ghost cells of this lane's column pair across a z face (d = 0 below, 1 above)
@@ -559,13 +554,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             // ---- x faces
             {
                 const double2* bf = bfp + ((xq >> 1) * 8 + yy);
-                double2        b0 = make_double2(0.0, 0.0), b1 = b0, b2 = b0;
-                if (!PREDPARK || xq == 0 || xq == 3)
-                {
-                    b0 = bf[0];
-                    b1 = bf[32];
-                    b2 = bf[64];
-                }
+                const double2  b0 = bf[0], b1 = bf[32], b2 = bf[64];
                 const double   bfl[NV] = { b0.x, b0.y, b1.x, b1.y, b2.x };
                 Cell3          L;
 #pragma unroll
@@ -607,16 +596,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 flux3<1>(YA, nw.A, GyA);
                 flux3<1>(YB, nw.B, GyB);
                 const double2* bf = bfp + ((2 + (yy >> 2)) * 8 + 2 * xq);
-                double2        c0 = make_double2(0.0, 0.0), c1 = c0, c2 = c0, d0 = c0, d1 = c0, d2 = c0;
-                if (!PREDPARK || yy == 0 || yy == 7)
-                {
-                    c0 = bf[0];
-                    c1 = bf[32];
-                    c2 = bf[64];
-                    d0 = bf[1];
-                    d1 = bf[33];
-                    d2 = bf[65];
-                }
+                const double2  c0 = bf[0], c1 = bf[32], c2 = bf[64], d0 = bf[1], d1 = bf[33], d2 = bf[65];
                 const double  bA[NV] = { c0.x, c0.y, c1.x, c1.y, c2.x };
                 const double  bB[NV] = { d0.x, d0.y, d1.x, d1.y, d2.x };
 #pragma unroll

@@ -145,7 +145,14 @@ advect3d_dense_kernel(const __grid_constant__ StepArgs a, int n_items)
                 const int  sy = co ? qy * HF + fy / 2 : (none ? iy : fy);
                 const int  sx = co ? qx * HF + fx / 2 : (none ? ix : fx);
                 const size_t o = (size_t)(none ? p : nq) * N + (size_t)sz * SS + sy * S + sx;
-                cp_async8(gdst + e, cur + o);
+                // a y- ghost row of a same-level neighbor is 8 contiguous cells: two per copy (the load / store
+                // unit works per REQUEST: scattered 8-byte copies, not bytes, are what these gathers cost)
+                if (sd && !co)
+                {
+                    if ((t & 1) == 0) cp_async16(gdst + e, cur + o);
+                }
+                else
+                    cp_async8(gdst + e, cur + o);
             }
         }
         cp_async_commit();

@@ -146,6 +146,7 @@ struct GhostSrc3
     int zbase;  // single source: plane zbase + (z >> zshift); finer: plane H + 2 (z mod S/2)
     int zshift;
     int finer;
+    int pair;   // dense kernel: y-side ghost row of a same-level neighbor (contiguous: two cells per copy)
 };
 
 template <int S, int H, int CR, int NS, int WPC>
@@ -397,6 +398,7 @@ euler3d_march_kernel(const __grid_constant__ StepArgs a, int n_items)
             else
                 f_y += (side & 1) ? -S : S;
             gs.finer  = 0;
+            gs.pair   = 0;
             gs.zshift = 0;
             gs.zbase  = H;
             if (rel == 0)

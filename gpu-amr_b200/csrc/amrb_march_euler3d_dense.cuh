@@ -233,15 +233,20 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
                 f_y += (side & 1) ? -S : S;
         }
         gs.finer  = 0;
+        gs.pair   = 0;
         gs.zshift = 0;
         gs.zbase  = 0;
         gs.q0 = gs.q1 = p;
         if (internal)
-            gs.off = g_y * S + g_x; // block side inside the patch: the own patch's cell
+        {
+            gs.off  = g_y * S + g_x; // block side inside the patch: the own patch's cell
+            gs.pair = (side >= 2);
+        }
         else if (rel == 1)
         {
             gs.q0 = gs.q1 = bnb.x; // same_t (patch_utils.hpp:315-332)
             gs.off        = f_y * S + f_x;
+            gs.pair       = (side >= 2); // a contiguous row of 8 cells: two per copy, even lanes only
         }
         else if (rel == 3)
         {
@@ -278,9 +283,22 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
         }
         else
         {
+            // the load / store unit works per REQUEST (scattered 8-byte copies, not bytes or cache lines, are what
+            // these gathers cost: profiles/r02_summary.md): the contiguous y-side rows go two cells per copy
             const size_t o = (size_t)gs.q0 * N + (size_t)(gs.zbase + (z >> gs.zshift)) * SS + gs.off;
+            if (gs.pair)
+            {
+                if ((bt & 1) == 0)
+                {
 #pragma unroll
-            for (int f = 0; f < NV; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
+                    for (int f = 0; f < NV; ++f) cp_async16(st + f * 32, a.cur.p[f] + o);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int f = 0; f < NV; ++f) cp_async8(st + f * 32, a.cur.p[f] + o);
+            }
         }
     };
     // source of the ghost cells of this lane's column pair across a z face (d = 0 below, 1 above)

@@ -90,8 +90,10 @@ struct DenseInst
                 else
                     march<4, 2, 4, 2>(st, a, n_items);
             }
+            else if (a.variant == 21)
+                march<2, 4, 4, 2>(st, a, n_items); // 2-plane chunks: 4.49 ms per 1.34e8 cells
             else
-                march<1, 4, 4, 2>(st, a, n_items);
+                march<1, 4, 4, 2>(st, a, n_items); // 16^3: 1-plane chunks of the block's 8 x 8 tile, 4 stages: 3.69 ms
         }
         else
         {

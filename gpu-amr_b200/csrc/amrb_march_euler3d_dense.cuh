@@ -31,7 +31,7 @@ struct March3DenseCfg
     static constexpr int NBX   = S / 8, NBY = S / 8;
     static constexpr int NB    = NBX * NBY;            // tasks (8 x 8 column blocks) per patch
     static constexpr bool WHOLE = (NB == 1);           // stream whole planes with TMA bulk copies
-    static constexpr int PLD   = WHOLE ? SS : 8 * S;   // doubles per staged field-plane (block rows, full width)
+    static constexpr int PLD   = 64;                   // doubles per staged field-plane: the block's 8 x 8 cells
     static constexpr int NCH   = S / CR;               // chunks per task
     static constexpr int FS    = CR * PLD;             // field stride inside a stage
     static constexpr int STAGE = NV * FS;
@@ -153,20 +153,17 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
         }
         else
         {
-            // wider patches: the block's 8 rows of a field-plane (full row width, 8 S contiguous
-            // doubles) moved as 16-byte cp.async pieces by all lanes, which then arrive on the stage's
-            // mbarrier (32 arrivals per phase)
-            const size_t go = (size_t)p * N + (size_t)(ic * CR) * SS + (size_t)(8 * by) * S;
+            // wider patches: the block's 8 rows x 8 cells of a field-plane (64-byte row pieces at the patch's row
+            // pitch) moved as ONE 16-byte cp.async piece per lane into the same dense 8 x 8 tile the 8^3 path
+            // stages (the cells left and right of the block are boundary faces of the task: they come through the
+            // ghost gathers), then the lanes arrive on the stage's mbarrier (32 arrivals per phase)
+            const size_t go = (size_t)p * N + (size_t)(ic * CR) * SS + (size_t)(8 * by + (lane >> 2)) * S + 8 * bx +
+                              2 * (lane & 3);
 #pragma unroll
             for (int f = 0; f < NV; ++f)
 #pragma unroll
                 for (int j = 0; j < CR; ++j)
-                {
-                    const double* src = a.cur.p[f] + go + (size_t)j * SS;
-                    double*       d   = dst + f * FS + j * PLD;
-#pragma unroll
-                    for (int i = lane; i < PLD / 2; i += 32) cp_async16(d + 2 * i, src + 2 * i);
-                }
+                    cp_async16(dst + f * FS + j * PLD + 2 * lane, a.cur.p[f] + go + (size_t)j * SS);
             cp_async_mbar_arrive(&bar[ist]);
         }
         if (++ic == C::NCH)
@@ -422,7 +419,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
         const int    x0 = 8 * bx, y0 = 8 * by; // interior coordinates of the block's first cell
         if constexpr (!PF) resolve_gs(tab, p, bx, by);
         // interior cell of this lane's boundary face inside the staged block rows
-        const int ioff_s = (side < 2) ? bt * S + (side ? x0 + 7 : x0) : ((side == 3) ? 7 : 0) * S + x0 + bt;
+        const int ioff_s = (side < 2) ? bt * 8 + (side ? 7 : 0) : ((side == 3) ? 7 : 0) * 8 + bt;
         // flux of this lane's boundary face of plane z: ghost cell from the staging column, interior
         // cell from the staged plane (`pl` = first field of that plane inside the ring) -> sBF[z & 1].
         // G = F(ghost) + F(interior) -/+ smax (U_interior - U_ghost), one branch-free form for all sides.
@@ -542,8 +539,8 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             else
                 zghost(1, tab, p, bx, by, gzA, gzB); // in flight during the last plane
             if (sl == 0) mbar_wait(&bar[cst], cph);
-            const double* src = ring + cst * C::STAGE + sl * PLD + yy * S + x0 + 2 * xq;
-            const int     lo  = (x0 + 2 * xq > 0) ? -1 : 0; // left cell (clamped: replaced by a parked flux)
+            const double* src = ring + cst * C::STAGE + sl * PLD + yy * 8 + 2 * xq; // the staged tile is 8 x 8
+            const int     lo  = (xq > 0) ? -1 : 0; // left cell (clamped: replaced by a parked flux)
             double        Lu[NV];
 #pragma unroll
             for (int f = 0; f < NV; ++f)
@@ -595,7 +592,7 @@ __device__ __forceinline__ void euler3d_dense_body(const StepArgs& a, int n_item
             }
             // ---- y faces
             {
-                const int yl = (yy > 0) ? -S : 0; // staged row below (clamped: replaced by a parked flux)
+                const int yl = (yy > 0) ? -8 : 0; // staged row below (clamped: replaced by a parked flux)
                 Cell3     YA, YB;
 #pragma unroll
                 for (int f = 0; f < NV; ++f)
